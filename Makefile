@@ -1,0 +1,34 @@
+# Builds the C-ABI library (hand-written sm_100a CUDA) and the C oracle pieces.
+# `python -c "import __graft_entry__ as g; g.build()"` drives this.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo --use_fast_math -Xcompiler -fPIC,-Wall,-Wno-unused-function \
+             -Xptxas -v --cudart static -Iinclude
+CSRC      := xpretrain_b200/csrc
+LIBDIR    := xpretrain_b200/lib
+OBJDIR    := build/obj
+SRCS      := $(wildcard $(CSRC)/*.cu)
+OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
+LIB       := $(LIBDIR)/libxpretrain_b200.so
+
+all: $(LIB)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/xpretrain_b200.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+	@grep -E "error|warning|spill" $(OBJDIR)/$*.ptxas.log | grep -v "0 bytes spill" | head -20 || true
+
+$(LIB): $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared --cudart static -o $@ $(OBJS)
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all clean
+
+# standalone GPU self-tests (no torch); run on the GPU box
+TOOLS := build/gemm_selftest
+tools: $(LIB) $(TOOLS)
+build/gemm_selftest: tools/gemm_selftest.cu $(LIB)
+	$(NVCC) $(ARCH) -O2 -std=c++17 --cudart static -Iinclude $< -o $@ -L$(LIBDIR) -lxpretrain_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(LIBDIR)'

@@ -1,0 +1,411 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring
+//   -> tcgen05.mma (single issuing thread, fp32 accumulators in TMEM, double buffered)
+//   -> tcgen05.ld epilogue (bias / q-scale / QuickGELU / dQuickGELU / residual) -> global.
+// One CTA per SM, 8 warps: warp0 = TMA producer, warp1 = MMA issuer,
+// warp2 = TMEM allocator, warps 4..7 = epilogue (one TMEM lane quarter each).
+//
+// Replaces (see include/xpretrain_b200.h) every nn.Linear forward/backward on
+// the CLIP-ViP hot path: CLIP_ViP.py:341-343,379,393-395,1141-1145 and the
+// patch-embedding conv :178 (as an im2col GEMM).
+#include "../../include/xpretrain_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace xp {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmDev {
+  void* c;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* aux;
+  int M, N, K;
+  long long ldc, ldr, ld_aux;
+  int act;
+  int splits;
+  int scale_cols;
+  float alpha, col_scale;
+  uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes): 64-element atom stride, 8-k-row group stride
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  // ring + 1 KiB alignment slack + barriers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float act_gelu_erf_grad(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <int BN, int A_MN, int B_MN, int OUT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_mn = num_m * num_n;
+  const int total = num_mn * p.splits;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per = (kb_total + p.splits - 1) / p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int split = tile / num_mn;
+        const int mn = tile - split * num_mn;
+        const int m_blk = mn / num_n;
+        const int n_blk = mn - m_blk * num_n;
+        const int k0 = split * kb_per;
+        const int k1 = min(kb_total, k0 + kb_per);
+        for (int kb = k0; kb < k1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_2d(sA + i * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+          } else {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sB + i * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+          } else {
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int split = tile / num_mn;
+        const int k0 = split * kb_per;
+        const int k1 = min(kb_total, k0 + kb_per);
+        if (k0 >= k1) continue;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = k0; kb < k1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / UMMA_K; ++j) {
+            // K-major: 16 elements = 32 B further along the swizzled row; 8-row groups 1024 B apart.
+            // MN-major: 16 k-rows = 2048 B further; 64-element MN atoms BK*128 B apart.
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sA + j * (UMMA_K * 128), p.mn_lbo, p.mn_sbo)
+                                        : make_smem_desc_sw128(sA + j * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sB + j * (UMMA_K * 128), p.mn_lbo, p.mn_sbo)
+                                        : make_smem_desc_sw128(sB + j * (UMMA_K * 2), 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > k0 || j > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------- epilogue
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int split = tile / num_mn;
+      const int mn = tile - split * num_mn;
+      const int m_blk = mn / num_n;
+      const int n_blk = mn - m_blk * num_n;
+      const int k0 = split * kb_per;
+      const int k1 = min(kb_total, k0 + kb_per);
+      if (k0 >= k1) continue;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (row_ok && n0 < p.N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            if (n >= p.N) break;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
+            if (p.bias != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (n < p.scale_cols) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] *= p.col_scale;
+            }
+            if (p.act == XP_ACT_QUICK_GELU || p.act == XP_ACT_GELU_ERF) {
+              if (p.aux != nullptr) {
+                uint4 h;
+                h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]);
+                h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
+                *reinterpret_cast<uint4*>(p.aux + static_cast<long long>(row) * p.ld_aux + n) = h;
+              }
+              if (p.act == XP_ACT_QUICK_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = act_gelu_erf(v[i]);
+              }
+            } else if (p.act == XP_ACT_DQUICK_GELU || p.act == XP_ACT_DGELU_ERF) {
+              const uint4 h = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(row) * p.ld_aux + n);
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+              if (p.act == XP_ACT_DQUICK_GELU) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  v[2 * i] *= quick_gelu_grad(bf16_lo(hw[i]));
+                  v[2 * i + 1] *= quick_gelu_grad(bf16_hi(hw[i]));
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  v[2 * i] *= act_gelu_erf_grad(bf16_lo(hw[i]));
+                  v[2 * i + 1] *= act_gelu_erf_grad(bf16_hi(hw[i]));
+                }
+              }
+            }
+            if (p.residual != nullptr) {
+              const uint4 q = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + n);
+              const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[2 * i] += bf16_lo(qw[i]);
+                v[2 * i + 1] += bf16_hi(qw[i]);
+              }
+            }
+            if (OUT == XP_OUT_BF16) {
+              uint4 o;
+              o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+              o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + static_cast<long long>(row) * p.ldc + n) = o;
+            } else if (OUT == XP_OUT_F32) {
+              float* dst = static_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + n;
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              float* dst = static_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + n;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]),
+                           "f"(v[2]), "f"(v[3])
+                           : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]),
+                           "f"(v[6]), "f"(v[7])
+                           : "memory");
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int A_MN, int B_MN, int OUT>
+static int launch_gemm(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev, int grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    XP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, dev);
+  XP_CHECK_LAUNCH("gemm_kernel");
+  return 0;
+}
+
+template <int BN, int OUT>
+static int dispatch_layout(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev,
+                           int grid, cudaStream_t stream) {
+  if (g->a_layout == 0 && g->b_layout == 0) return launch_gemm<BN, 0, 0, OUT>(g, tmA, tmB, dev, grid, stream);
+  if (g->a_layout == 0 && g->b_layout == 1) return launch_gemm<BN, 0, 1, OUT>(g, tmA, tmB, dev, grid, stream);
+  if (g->a_layout == 1 && g->b_layout == 1) return launch_gemm<BN, 1, 1, OUT>(g, tmA, tmB, dev, grid, stream);
+  if (g->a_layout == 1 && g->b_layout == 0) return launch_gemm<BN, 1, 0, OUT>(g, tmA, tmB, dev, grid, stream);
+  return fail("xp_gemm: a_layout/b_layout must be 0 or 1");
+}
+
+template <int BN>
+static int dispatch_out(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev, int grid,
+                        cudaStream_t stream) {
+  switch (g->out) {
+    case XP_OUT_BF16: return dispatch_layout<BN, XP_OUT_BF16>(g, tmA, tmB, dev, grid, stream);
+    case XP_OUT_F32: return dispatch_layout<BN, XP_OUT_F32>(g, tmA, tmB, dev, grid, stream);
+    case XP_OUT_F32_ATOMIC: return dispatch_layout<BN, XP_OUT_F32_ATOMIC>(g, tmA, tmB, dev, grid, stream);
+  }
+  return fail("xp_gemm: bad out mode");
+}
+
+static int g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0;
+}  // namespace xp
+
+// Debug hook for tools/gemm_selftest (not part of the public ABI).
+extern "C" void xp_debug_gemm_mn_desc(int lbo, int sbo) {
+  xp::g_dbg_mn_lbo = lbo;
+  xp::g_dbg_mn_sbo = sbo;
+}
+
+extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
+  using namespace xp;
+  if (!g) return fail("xp_gemm: null args");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return fail("xp_gemm: M, N, K must be positive");
+  if (g->N % 8 != 0) return fail("xp_gemm: N must be a multiple of 8");
+  if (!g->a || !g->b || !g->c) return fail("xp_gemm: null operand");
+  const int splits = g->splits <= 0 ? 1 : g->splits;
+  if (splits > 1 && g->out != XP_OUT_F32_ATOMIC) return fail("xp_gemm: split-K requires XP_OUT_F32_ATOMIC");
+  if ((g->act == XP_ACT_DQUICK_GELU || g->act == XP_ACT_DGELU_ERF) && !g->aux)
+    return fail("xp_gemm: dGELU epilogue needs aux (the forward pre-activation)");
+  const int elem_c = g->out == XP_OUT_BF16 ? 2 : 4;
+  if ((reinterpret_cast<uintptr_t>(g->c) & 15) || (g->ldc * elem_c) % 16)
+    return fail("xp_gemm: C must be 16-byte aligned with a 16-byte multiple row pitch");
+  if (g->bias && (reinterpret_cast<uintptr_t>(g->bias) & 15)) return fail("xp_gemm: bias must be 16-byte aligned");
+  if (g->residual && ((reinterpret_cast<uintptr_t>(g->residual) & 15) || (g->ldr % 8)))
+    return fail("xp_gemm: residual must be 16-byte aligned, ldr % 8 == 0");
+  if (g->aux && ((reinterpret_cast<uintptr_t>(g->aux) & 15) || (g->ld_aux % 8)))
+    return fail("xp_gemm: aux must be 16-byte aligned, ld_aux % 8 == 0");
+
+  const int nsm = sm_count();
+  const int num_m = static_cast<int>((g->M + BM - 1) / BM);
+  int bn = g->block_n;
+  if (bn == 0) {
+    const long long tiles256 = static_cast<long long>(num_m) * ((g->N + 255) / 256) * splits;
+    bn = (g->N >= 256 && tiles256 >= nsm) ? 256 : 128;
+  }
+  if (bn != 128 && bn != 256) return fail("xp_gemm: block_n must be 0, 128 or 256");
+  const long long total = static_cast<long long>(num_m) * ((g->N + bn - 1) / bn) * splits;
+  int grid = g->max_ctas > 0 ? g->max_ctas : nsm;
+  if (grid > total) grid = static_cast<int>(total);
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (g->a_layout == 0)
+    rc = make_tmap_bf16_2d(&tmA, g->a, g->K, g->M, g->lda, BK, BM);
+  else
+    rc = make_tmap_bf16_2d(&tmA, g->a, g->M, g->K, g->lda, 64, BK);
+  if (rc) return rc;
+  if (g->b_layout == 0)
+    rc = make_tmap_bf16_2d(&tmB, g->b, g->K, g->N, g->ldb, BK, bn);
+  else
+    rc = make_tmap_bf16_2d(&tmB, g->b, g->N, g->K, g->ldb, 64, BK);
+  if (rc) return rc;
+
+  GemmDev dev;
+  dev.c = g->c;
+  dev.bias = g->bias;
+  dev.residual = static_cast<const __nv_bfloat16*>(g->residual);
+  dev.aux = static_cast<__nv_bfloat16*>(g->aux);
+  dev.M = static_cast<int>(g->M);
+  dev.N = static_cast<int>(g->N);
+  dev.K = static_cast<int>(g->K);
+  dev.ldc = g->ldc;
+  dev.ldr = g->ldr;
+  dev.ld_aux = g->ld_aux;
+  dev.act = g->act;
+  dev.splits = splits;
+  dev.scale_cols = g->scale_cols;
+  dev.alpha = g->alpha;
+  dev.col_scale = g->col_scale;
+  dev.mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : BK * 128;
+  dev.mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024;
+
+  return bn == 256 ? dispatch_out<256>(g, tmA, tmB, dev, grid, stream)
+                   : dispatch_out<128>(g, tmA, tmB, dev, grid, stream);
+}
