@@ -1,0 +1,100 @@
+"""CPU: the oracle (oracle/clipvip_oracle.py) replays the golden vectors that
+tests/golden/make_golden.py produced from the real reference modules."""
+import os
+
+import pytest
+import torch
+
+from oracle import clipvip_oracle as O
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _cfg(meta):
+    return O.ClipVipCfg(vision=O.TowerCfg(768, 12, meta["vision_layers"], 3072),
+                        text=O.TowerCfg(512, 8, meta["text_layers"], 2048))
+
+
+def _replay(gold, need_grads):
+    meta = gold["meta"]
+    cfg = _cfg(meta)
+    sd = O.init_state_dict(cfg, seed=meta["weight_seed"])
+    video, ids, mask = O.synthetic_batch(meta["B"], meta["T"], meta["Lt"], cfg, seed=meta["data_seed"],
+                                         ragged_text=meta["ragged"])
+    assert torch.equal(ids, gold["input_ids"]) and torch.equal(mask, gold["attention_mask"])
+    assert abs(float(video.double().sum()) - gold["video_checksum"]) < 1e-6 * video.numel() ** 0.5
+    if need_grads:
+        sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    return cfg, sd, video, ids, mask
+
+
+def test_depth2_ragged_forward_hidden_and_grads(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "depth2_b3_t12_ragged.pt"), weights_only=False)
+    cfg, sd, video, ids, mask = _replay(gold, need_grads=True)
+    pooled_v, vh = O.vision_tower(sd, video, cfg, return_hidden=True)
+    pooled_t, th = O.text_tower(sd, ids, mask, cfg, return_hidden=True)
+    got_rows = torch.stack([torch.cat([h[:, :8], h[:, -4:]], 1).detach() for h in vh])
+    assert _rel(got_rows, gold["vision_hidden_rows"]) < 1e-5
+    assert _rel(torch.stack([h.detach() for h in th]), gold["text_hidden"]) < 1e-5
+    out = O.clip_vip_forward(sd, video, ids, mask, cfg)
+    assert _rel(out["vis_features"].detach(), gold["vis_features"]) < 1e-5
+    assert _rel(out["text_features"].detach(), gold["text_features"]) < 1e-5
+    loss = O.nce_learnable_temp_loss(out["vis_features"], out["text_features"], sd["logit_scale"])
+    assert abs(float(loss) - float(gold["loss"])) < 1e-5 * abs(float(gold["loss"]))
+    loss.backward()
+    for k, gn in gold["grad_norms"].items():
+        if gn > 1e-5:
+            assert abs(float(sd[k].grad.norm()) - gn) < 1e-3 * gn, k
+    for k, sample in gold["grad_samples"].items():
+        assert _rel(sd[k].grad.flatten()[:256], sample) < 1e-3, k
+
+
+@pytest.mark.timeout(600)
+def test_cfg1_full_depth_forward(golden_dir):
+    """BASELINE.json configs[0]: ViT-B/16, B=2, T=4 (temporal interpolation 12 -> 4), 32 tokens, fp32 CPU."""
+    gold = torch.load(os.path.join(golden_dir, "cfg1_b2_t4.pt"), weights_only=False)
+    cfg, sd, video, ids, mask = _replay(gold, need_grads=False)
+    with torch.no_grad():
+        out = O.clip_vip_forward(sd, video, ids, mask, cfg)
+        loss = O.nce_learnable_temp_loss(out["vis_features"], out["text_features"], sd["logit_scale"])
+    assert _rel(out["vis_features"], gold["vis_features"]) < 1e-5
+    assert _rel(out["text_features"], gold["text_features"]) < 1e-5
+    assert abs(float(loss) - float(gold["loss"])) < 1e-5 * abs(float(gold["loss"]))
+
+
+def test_nce_loss_gather_and_closed_form(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "nce_loss_w4.pt"), weights_only=False)
+    V = O.gather_rank_major(gold["vis_per_rank"])
+    T = O.gather_rank_major(gold["txt_per_rank"])
+    loss = O.nce_learnable_temp_loss(V, T, gold["logit_scale"])
+    assert abs(float(loss) - float(gold["loss"])) < 1e-6
+    dv, dt, dl = O.nce_closed_form_grads(V, T, gold["logit_scale"])
+    assert _rel(dv, gold["d_vis"]) < 1e-5 and _rel(dt, gold["d_txt"]) < 1e-5
+    assert abs(float(dl) - float(gold["d_logit_scale"])) < 1e-5
+
+
+def test_vip_attention_equals_block_masked_dense():
+    """forward2 == dense attention under allow[i,j] = global(i) | global(j) | frame(i)==frame(j)."""
+    torch.manual_seed(3)
+    heads, C, M, T, L = 2, 32, 4, 3, 5
+    S = M + T * L
+    sd = {}
+    for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+        sd[f"a.{n}.weight"] = torch.randn(C, C, dtype=torch.float64) * 0.2
+        sd[f"a.{n}.bias"] = torch.randn(C, dtype=torch.float64) * 0.1
+    x = torch.randn(2, S, C, dtype=torch.float64)
+    got = O.vip_attention(sd, x, "a.", heads, (M, T, L))
+    frame = torch.cat([torch.full((M,), -1), torch.arange(T).repeat_interleave(L)])
+    allow = (frame[:, None] < 0) | (frame[None, :] < 0) | (frame[:, None] == frame[None, :])
+    add = torch.zeros(S, S, dtype=torch.float64).masked_fill(~allow, float("-inf"))[None, None]
+    want = O.dense_attention(sd, x, "a.", heads, add)
+    assert _rel(got, want) < 1e-12
+
+
+def test_flop_model_matches_baseline_md():
+    f = O.flops_per_pair(O.ClipVipCfg(), T=12, Lt=32)
+    assert abs(f["fwd"] / 1e9 - 423.12) < 0.05
+    assert abs(f["train"] / 1e9 - 1266.58) < 0.2
+    assert abs(f["vip_block_fwd"] / 1e9 - 34.825) < 0.01

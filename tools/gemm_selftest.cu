@@ -242,7 +242,9 @@ int main(int argc, char** argv) {
       {"epi_dgelu", 512, 3072, 768, 0, 1, XP_ACT_DQUICK_GELU, XP_OUT_BF16, 1, 256, false, false, false},
       {"epi_residual", 512, 768, 3072, 0, 0, 0, XP_OUT_BF16, 1, 128, true, true, false},
   };
-  for (const Case& c : basic) fails += run_case(c, false);
+  const char* only = (argc > 2 && !strcmp(argv[1], "only")) ? argv[2] : nullptr;
+  if (!only)
+    for (const Case& c : basic) fails += run_case(c, false);
 
   if (argc > 1 && !strcmp(argv[1], "mnsweep")) {
     // If MN-major failed above, try the alternative LBO/SBO reading.
@@ -273,7 +275,8 @@ int main(int argc, char** argv) {
       {"perf_square", 8192, 8192, 8192, 0, 0, 0, XP_OUT_BF16, 1, 256, false, false, false},
   };
   if (!(argc > 1 && !strcmp(argv[1], "quick")))
-    for (const Case& c : perf) fails += run_case(c, true);
+    for (const Case& c : perf)
+      if (!only || !strcmp(only, c.name)) fails += run_case(c, true);
   printf("gemm_selftest: %d failing case(s)\n", fails);
   return fails ? 1 : 0;
 }
