@@ -60,11 +60,109 @@ typedef struct XpGemm {
   int32_t splits;     /* split-K factor (>1 only with XP_OUT_F32_ATOMIC) */
   int32_t scale_cols; /* columns [0, scale_cols) are multiplied by col_scale */
   float alpha, col_scale;
+  /* Optional grouped row addressing (0 = plain row*ld): element offset of row r is
+   *   (r / group) * group_stride + (r % group) * ld.
+   * C (and aux) use c_group; residual uses r_group (r_group_stride = 0 makes the residual a
+   * periodic [r_group, N] table, used for the patch-embedding position+temporal add). */
+  int64_t c_group, c_group_stride, r_group, r_group_stride;
   int32_t block_n;    /* 0 = auto, else 128 or 256 */
   int32_t max_ctas;   /* 0 = one persistent CTA per SM */
 } XpGemm;
 
 int xp_gemm(const XpGemm* g, void* stream);
+
+/* ------------------------------------------------------------- row kernels --
+ * Row addressing shared by the row-wise kernels: element offset of logical row r is
+ *   offsets[r]                                            if offsets != NULL (device i64 array)
+ *   (r / group) * group_stride + (r % group) * ld         if group > 0
+ *   r * ld                                                otherwise.
+ * This is how the kernels skip the M global tokens of each video, pick the CLS row
+ * (CLIP_ViP.py:891) or the EOS row (CLIP_ViP.py:776) without a gather copy. */
+typedef struct XpRowMap {
+  int64_t group, group_stride, ld;
+  const int64_t* offsets;
+} XpRowMap;
+
+/* nn.LayerNorm forward (CLIP_ViP.py:447,458,881,892,771): bf16 in/out, fp32 gamma/beta/statistics. */
+int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMap* ymap, const float* gamma,
+                     const float* beta, float* mean, float* rstd, int64_t rows, int32_t C, float eps, void* stream);
+/* LayerNorm backward; dx = LN'(dy) + dres (the residual-branch gradient, may be NULL);
+ * dgamma/dbeta are ACCUMULATED (fp32 atomics) so they can point at .grad buffers. */
+int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const void* x, const XpRowMap* xmap, const float* gamma,
+                     const float* mean, const float* rstd, const void* dres, const XpRowMap* drmap, void* dx,
+                     const XpRowMap* dxmap, float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream);
+/* x / x.norm(dim=-1, keepdim=True) (CLIP_ViP.py:1148-1149), fp32. */
+int xp_l2norm_fwd(const float* x, float* y, float* inv_norm, int32_t rows, int32_t C, void* stream);
+int xp_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, void* dx_bf16, int32_t rows, int32_t C,
+                  float scale, void* stream);
+/* out[c] += scale * sum_r x[r,c]: bias gradients of every nn.Linear. */
+int xp_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int32_t C, float scale, void* stream);
+/* fp32 master parameter -> bf16 compute copy. */
+int xp_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------- embeddings --*/
+enum { XP_DTYPE_F32 = 0, XP_DTYPE_BF16 = 1, XP_DTYPE_F16 = 2 };
+
+/* im2col of nn.Conv2d(3, width, kernel=stride=patch, bias=False) (CLIP_ViP.py:157-159,178-179):
+ * video [frames,3,H,W] -> patches bf16 [frames*(H/p)*(W/p), 3*p*p]; the conv itself then runs as xp_gemm. */
+int xp_vip_patchify(const void* video, int32_t dtype, void* patches_bf16, int64_t frames, int32_t H, int32_t W,
+                    int32_t patch, void* stream);
+/* CLIP_ViP.py:170-176,183-195: table[t*L+l] = interp(temporal_embedding)[t] + position_embedding[1+l] (bf16,
+ * [T*L, C]) and the M = 1 + add_cls_num global rows x[b, m] = (class_embedding | added_cls[m-1]) + position_embedding[0]
+ * written into x_bf16 [B, M+T*L, C].  temporal may be NULL (if_use_temporal_embed = 0). */
+int xp_vip_embed_tables(const float* pos, const float* temporal, const float* cls, const float* added,
+                        void* table_bf16, void* x_bf16, int32_t B, int32_t T, int32_t L, int32_t M, int32_t C,
+                        int32_t temporal_size, void* stream);
+/* Backward of the above: d_patch bf16 [B, T*L, C] and d_global bf16 [B, M, C] (the two compact halves of
+ * d_embeddings) accumulated (fp32) into the four parameter gradients. */
+int xp_vip_embed_bwd(const void* d_patch_bf16, const void* d_global_bf16, float* d_pos, float* d_temporal, float* d_cls,
+                     float* d_added, int32_t B, int32_t T, int32_t L, int32_t M, int32_t C, int32_t temporal_size,
+                     void* stream);
+/* CLIPTextEmbeddings.forward (CLIP_ViP.py:222-225): x[r] = token_embedding[ids[r]] + position_embedding[r % Lt].
+ * ids are int64 and indexed bit-exactly; *err_flag is set to 1 if any id is outside [0, vocab). */
+int xp_text_embed_fwd(const int64_t* ids, const float* tok, const float* pos, void* x_bf16, int32_t rows, int32_t Lt,
+                      int32_t C, int32_t vocab, int32_t* err_flag, void* stream);
+int xp_text_embed_bwd(const int64_t* ids, const void* dx_bf16, float* d_tok, float* d_pos, int32_t rows, int32_t Lt,
+                      int32_t C, int32_t vocab, void* stream);
+/* EOS pooling row (CLIP_ViP.py:776): offsets[b] = (b*Lt + first argmax_s ids[b,s]) * C; index[b] optional. */
+int xp_eos_offsets(const int64_t* ids, int64_t* offsets, int32_t* index, int32_t B, int32_t Lt, int32_t C,
+                   void* stream);
+
+/* ------------------------------------------------------------ ViP attention --
+ * CLIPAttention.forward2 (CLIP_ViP.py:332-381) between the QKV projection and out_proj.
+ *   qkv  bf16 [B*S, 3C]  columns [q | k | v], head h at [h*64, h*64+64), q already scaled by 64**-0.5
+ *   out  bf16 [B*S, C]   (the tensor out_proj consumes; rows ordered [M global, frame0 L, frame1 L, ...])
+ *   lse  f32  [B, H, S]  log-sum-exp of every query row (saved for backward)
+ * S = M + T*L, head_dim 64, M + L <= 208.  workspace: xp_vip_attention_workspace_bytes() bytes. */
+int64_t xp_vip_attention_workspace_bytes(int32_t B, int32_t H, int32_t T, int32_t M);
+int xp_vip_attention_fwd(const void* qkv, void* out, float* lse, float* workspace, int32_t B, int32_t H, int32_t T,
+                         int32_t L, int32_t M, int32_t C, void* stream);
+/* dqkv bf16 [B*S, 3C] = gradient w.r.t. the (un-scaled-q) projection outputs, i.e. the dq part already carries
+ * q_scale (CLIP_ViP.py:341), so the QKV dgrad/wgrad GEMMs treat the three thirds uniformly. */
+int xp_vip_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                         float* workspace, int32_t B, int32_t H, int32_t T, int32_t L, int32_t M, int32_t C,
+                         float q_scale, void* stream);
+
+/* ------------------------------------------------------- text-tower attention --
+ * CLIPAttention.forward (CLIP_ViP.py:266-330) between the QKV projection and out_proj, with the causal mask
+ * (CLIP_ViP.py:788-797) and the padding mask built from attention_mask int64 [B, Lt] (CLIP_ViP.py:50-61).
+ * qkv bf16 [B*Lt, 3C] (q pre-scaled), out bf16 [B*Lt, C], probs f32 [B, H, Lt, Lt] (saved for backward). Lt <= 96. */
+int xp_text_attention_fwd(const void* qkv, const int64_t* mask, void* out, float* probs, int32_t B, int32_t H,
+                          int32_t Lt, int32_t C, void* stream);
+int xp_text_attention_bwd(const void* qkv, const void* dout, const float* probs, void* dqkv, int32_t B, int32_t H,
+                          int32_t Lt, int32_t C, float q_scale, void* stream);
+
+/* ------------------------------------------------------------------ InfoNCE --
+ * NCELearnableTempLoss.forward (loss.py:134-141) on the gathered [N, d] fp32 embeddings.  The logits GEMM and the
+ * two gradient GEMMs run through xp_gemm; these are the pieces around them:
+ *   xp_nce_split:        x f32 [rows, d] -> x3 bf16 [rows, 3d] = [hi|hi|lo] (pattern 0) or [hi|lo|hi] (pattern 1),
+ *                        so that x3_a . x3_b^T = hi*hi + hi*lo + lo*hi (fp32-grade logits on bf16 tensor cores);
+ *                        hi_bf16 (optional) receives the plain bf16 copy used by the gradient GEMMs.
+ *   xp_nce_softmax_grad: z f32 [N, N] (row pitch ld, shared with g_scaled) = V T^T (unscaled) -> row/col LSE of exp(logit_scale)*z, the scalar loss
+ *                        (overwritten), d_logit_scale (ACCUMULATED) and g_scaled bf16 [N,N] = exp(logit_scale) * dL/dZ. */
+int xp_nce_split(const float* x, void* x3_bf16, void* hi_bf16, int32_t rows, int32_t d, int32_t pattern, void* stream);
+int xp_nce_softmax_grad(const float* z, const float* logit_scale, float* lse_rows, float* lse_cols, void* g_scaled_bf16,
+                        float* loss, float* d_logit_scale, int32_t N, int64_t ld, void* stream);
 
 #ifdef __cplusplus
 }

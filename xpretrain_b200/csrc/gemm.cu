@@ -2,8 +2,8 @@
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring
 //   -> tcgen05.mma (single issuing thread, fp32 accumulators in TMEM, double buffered)
 //   -> tcgen05.ld epilogue (bias / q-scale / QuickGELU / dQuickGELU / residual) -> global.
-// One CTA per SM, 8 warps: warp0 = TMA producer, warp1 = MMA issuer,
-// warp2 = TMEM allocator, warps 4..7 = epilogue (one TMEM lane quarter each).
+// One CTA per SM, 12 warps: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps 4..11 = epilogue (two warps per TMEM lane quarter, each taking half of the columns).
 //
 // Replaces (see include/xpretrain_b200.h) every nn.Linear forward/backward on
 // the CLIP-ViP hot path: CLIP_ViP.py:341-343,379,393-395,1141-1145 and the
@@ -17,7 +17,8 @@ namespace xp {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
 
 struct GemmDev {
   void* c;
@@ -26,6 +27,7 @@ struct GemmDev {
   __nv_bfloat16* aux;
   int M, N, K;
   long long ldc, ldr, ld_aux;
+  long long c_group, c_group_stride, r_group, r_group_stride;
   int act;
   int splits;
   int scale_cols;
@@ -41,7 +43,7 @@ struct GemmCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
   // ring + 1 KiB alignment slack + barriers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 2 * BN * 4;
 };
 
 __device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -64,6 +66,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,7 +89,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -181,7 +184,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------- epilogue
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    // 8 warps: warp (4+e) owns TMEM lane quarter e&3 and column half e>>2 of every accumulator.
+    const int ew = warp - 4;
+    const int quarter = ew & 3;  // == warp % 4, the lane quarter this warp may read
+    const int half = ew >> 2;
+    const int etid = threadIdx.x - 128;  // 0..255
+    constexpr int CHUNKS = BN / 64;      // 32-column chunks per warp per tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -192,92 +200,117 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int k0 = split * kb_per;
       const int k1 = min(kb_total, k0 + kb_per);
       if (k0 >= k1) continue;
+      // stage this tile's bias slice in shared memory (double buffered by accumulator stage)
+      float* sbias = bias_smem + acc * BN;
+      for (int i = etid; i < BN; i += EPI_THREADS) {
+        const int n = n_blk * BN + i;
+        sbias[i] = (p.bias != nullptr && n < p.N && split == 0) ? p.bias[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
-        tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
+      long long c_off = 0, r_off = 0;
+      if (row_ok) {
+        c_off = p.c_group > 0 ? (row / p.c_group) * p.c_group_stride + (row % p.c_group) * p.ldc
+                              : static_cast<long long>(row) * p.ldc;
+        r_off = p.r_group > 0 ? (row / p.r_group) * p.r_group_stride + (row % p.r_group) * p.ldr
+                              : static_cast<long long>(row) * p.ldr;
+      }
+      const long long a_off = static_cast<long long>(row) * p.ld_aux;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+      uint32_t rbuf[2][32];
+      tmem_ld32(t_row, rbuf[0]);
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        uint32_t(&r)[32] = rbuf[c & 1];
+        tmem_ld_wait(r);
+        if (c + 1 < CHUNKS) tmem_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);  // overlaps the math below
+        const int nl = half * (BN / 2) + c * 32;  // column within the tile
+        const int n0 = n_blk * BN + nl;
         if (row_ok && n0 < p.N) {
+          // issue the global reads of this chunk first so their latency overlaps
+          uint4 rres[4], raux[4];
+          const bool need_aux_in = (p.act == XP_ACT_DQUICK_GELU || p.act == XP_ACT_DGELU_ERF);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int n = n0 + g * 8;
-            if (n >= p.N) break;
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * p.alpha;
-            if (p.bias != nullptr) {
-              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
-              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            if (n < p.N) {
+              if (p.residual != nullptr) rres[g] = *reinterpret_cast<const uint4*>(p.residual + r_off + n);
+              if (need_aux_in) raux[g] = *reinterpret_cast<const uint4*>(p.aux + a_off + n);
             }
-            if (n < p.scale_cols) {
+          }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] *= p.col_scale;
-            }
-            if (p.act == XP_ACT_QUICK_GELU || p.act == XP_ACT_GELU_ERF) {
-              if (p.aux != nullptr) {
-                uint4 h;
-                h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]);
-                h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
-                *reinterpret_cast<uint4*>(p.aux + static_cast<long long>(row) * p.ld_aux + n) = h;
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            if (n < p.N) {
+              float v[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + nl + g * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + nl + g * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaf(__uint_as_float(r[g * 8 + i]), p.alpha, bb[i]);
+              if (n < p.scale_cols) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= p.col_scale;
               }
-              if (p.act == XP_ACT_QUICK_GELU) {
+              if (p.act == XP_ACT_QUICK_GELU || p.act == XP_ACT_GELU_ERF) {
+                if (p.aux != nullptr) {
+                  uint4 h;
+                  h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]);
+                  h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
+                  *reinterpret_cast<uint4*>(p.aux + a_off + n) = h;
+                }
+                if (p.act == XP_ACT_QUICK_GELU) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
-              } else {
+                  for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = act_gelu_erf(v[i]);
+                  for (int i = 0; i < 8; ++i) v[i] = act_gelu_erf(v[i]);
+                }
+              } else if (need_aux_in) {
+                const uint32_t hw[4] = {raux[g].x, raux[g].y, raux[g].z, raux[g].w};
+                if (p.act == XP_ACT_DQUICK_GELU) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    v[2 * i] *= quick_gelu_grad(bf16_lo(hw[i]));
+                    v[2 * i + 1] *= quick_gelu_grad(bf16_hi(hw[i]));
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    v[2 * i] *= act_gelu_erf_grad(bf16_lo(hw[i]));
+                    v[2 * i + 1] *= act_gelu_erf_grad(bf16_hi(hw[i]));
+                  }
+                }
               }
-            } else if (p.act == XP_ACT_DQUICK_GELU || p.act == XP_ACT_DGELU_ERF) {
-              const uint4 h = *reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(row) * p.ld_aux + n);
-              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-              if (p.act == XP_ACT_DQUICK_GELU) {
+              if (p.residual != nullptr) {
+                const uint32_t qw[4] = {rres[g].x, rres[g].y, rres[g].z, rres[g].w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  v[2 * i] *= quick_gelu_grad(bf16_lo(hw[i]));
-                  v[2 * i + 1] *= quick_gelu_grad(bf16_hi(hw[i]));
+                  v[2 * i] += bf16_lo(qw[i]);
+                  v[2 * i + 1] += bf16_hi(qw[i]);
                 }
+              }
+              if (OUT == XP_OUT_BF16) {
+                uint4 o;
+                o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+                o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + c_off + n) = o;
+              } else if (OUT == XP_OUT_F32) {
+                float* dst = static_cast<float*>(p.c) + c_off + n;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
               } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  v[2 * i] *= act_gelu_erf_grad(bf16_lo(hw[i]));
-                  v[2 * i + 1] *= act_gelu_erf_grad(bf16_hi(hw[i]));
-                }
+                float* dst = static_cast<float*>(p.c) + c_off + n;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]),
+                             "f"(v[2]), "f"(v[3])
+                             : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]),
+                             "f"(v[6]), "f"(v[7])
+                             : "memory");
               }
-            }
-            if (p.residual != nullptr) {
-              const uint4 q = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(row) * p.ldr + n);
-              const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                v[2 * i] += bf16_lo(qw[i]);
-                v[2 * i + 1] += bf16_hi(qw[i]);
-              }
-            }
-            if (OUT == XP_OUT_BF16) {
-              uint4 o;
-              o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-              o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + static_cast<long long>(row) * p.ldc + n) = o;
-            } else if (OUT == XP_OUT_F32) {
-              float* dst = static_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + n;
-              *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
-              float* dst = static_cast<float*>(p.c) + static_cast<long long>(row) * p.ldc + n;
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]),
-                           "f"(v[2]), "f"(v[3])
-                           : "memory");
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]),
-                           "f"(v[6]), "f"(v[7])
-                           : "memory");
             }
           }
         }
@@ -398,6 +431,10 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
   dev.ldc = g->ldc;
   dev.ldr = g->ldr;
   dev.ld_aux = g->ld_aux;
+  dev.c_group = g->c_group;
+  dev.c_group_stride = g->c_group_stride;
+  dev.r_group = g->r_group;
+  dev.r_group_stride = g->r_group_stride;
   dev.act = g->act;
   dev.splits = splits;
   dev.scale_cols = g->scale_cols;

@@ -1,0 +1,373 @@
+// HBM-bound row kernels of the CLIP-ViP path: LayerNorm forward/backward (with the residual-gradient
+// add fused), L2 normalisation forward/backward, bias-gradient column sums, fp32->bf16 parameter casts.
+// One warp per row, 16-byte vector accesses, fp32 statistics.
+//
+// Reference ops replaced: nn.LayerNorm at CLIP_ViP.py:447,458 (layer_norm1/2), :881 (pre_layrnorm),
+// :892 (post_layernorm), :771 (final_layer_norm); `x / x.norm(dim=-1, keepdim=True)` at :1148-1149.
+#include "../../include/xpretrain_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace xp {
+
+struct RowMapDev {
+  long long group, group_stride, ld;
+  const long long* offsets;  // optional explicit element offset per row
+};
+__device__ __forceinline__ long long row_addr(const RowMapDev& m, long long r) {
+  if (m.offsets) return m.offsets[r];
+  if (m.group > 0) return (r / m.group) * m.group_stride + (r % m.group) * m.ld;
+  return r * m.ld;
+}
+static RowMapDev to_dev(const XpRowMap& m) {
+  RowMapDev d;
+  d.group = m.group;
+  d.group_stride = m.group_stride;
+  d.ld = m.ld;
+  d.offsets = reinterpret_cast<const long long*>(m.offsets);
+  return d;
+}
+
+constexpr int LN_MAX_VEC = 4;  // C <= 4 * 32 * 8 = 1024
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ LayerNorm forward
+__global__ void __launch_bounds__(128)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowMapDev xm, __nv_bfloat16* __restrict__ y, RowMapDev ym,
+              const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean_out,
+              float* __restrict__ rstd_out, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int nvec = C >> 3;
+  const __nv_bfloat16* xr = x + row_addr(xm, r);
+  float v[LN_MAX_VEC][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  __nv_bfloat16* yr = y + row_addr(ym, r);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c * 8), g1 = *reinterpret_cast<const float4*>(gamma + c * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + c * 8), b1 = *reinterpret_cast<const float4*>(beta + c * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+      *reinterpret_cast<uint4*>(yr + c * 8) = pack8(o);
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[r] = mean;
+    if (rstd_out) rstd_out[r] = rstd;
+  }
+}
+
+// ----------------------------------------------------------------- LayerNorm backward
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma;
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy  (fp32 atomics, one per column per CTA).
+constexpr int LNB_WARPS = 8;
+template <int NVEC>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 2)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const __nv_bfloat16* __restrict__ x, RowMapDev xm,
+              const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const __nv_bfloat16* __restrict__ dres, RowMapDev drm, __nv_bfloat16* __restrict__ dx, RowMapDev dxm,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
+  extern __shared__ float red[];  // [LNB_WARPS][2][C], gamma staged behind it
+  float* sgamma = red + LNB_WARPS * 2 * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = C >> 3;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sgamma[c] = gamma[c];
+  __syncthreads();
+  float ag[NVEC][8], ab[NVEC][8];
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+  for (long long r = static_cast<long long>(blockIdx.x) * LNB_WARPS + warp; r < rows;
+       r += static_cast<long long>(gridDim.x) * LNB_WARPS) {
+    const __nv_bfloat16* xr = x + row_addr(xm, r);
+    const __nv_bfloat16* dyr = dy + row_addr(dym, r);
+    const __nv_bfloat16* drr = dres ? dres + row_addr(drm, r) : nullptr;
+    const float mu = mean[r], rs = rstd[r];
+    uint4 xraw[NVEC], draw[NVEC], rraw[NVEC];
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        xraw[i] = *reinterpret_cast<const uint4*>(xr + c * 8);
+        draw[i] = *reinterpret_cast<const uint4*>(dyr + c * 8);
+        if (drr) rraw[i] = *reinterpret_cast<const uint4*>(drr + c * 8);
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float xv[8], dv[8];
+        unpack8(xraw[i], xv);
+        unpack8(draw[i], dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * rs;
+          const float g = dv[j] * sgamma[c * 8 + j];
+          s1 += g;
+          s2 += g * xh;
+          ag[i][j] += dv[j] * xh;
+          ab[i][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    __nv_bfloat16* dxr = dx + row_addr(dxm, r);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float xv[8], dv[8], o[8];
+        unpack8(xraw[i], xv);
+        unpack8(draw[i], dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * rs;
+          o[j] = rs * (dv[j] * sgamma[c * 8 + j] - s1 - xh * s2);
+        }
+        if (drr) {
+          float rv[8];
+          unpack8(rraw[i], rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+        }
+        *reinterpret_cast<uint4*>(dxr + c * 8) = pack8(o);
+      }
+    }
+  }
+  // block reduction of the parameter gradients
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red[(warp * 2 + 0) * C + c * 8 + j] = ag[i][j];
+        red[(warp * 2 + 1) * C + c * 8 + j] = ab[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < LNB_WARPS; ++w) {
+      sg += red[(w * 2 + 0) * C + c];
+      sb += red[(w * 2 + 1) * C + c];
+    }
+    atomicAdd(dgamma + c, sg);
+    atomicAdd(dbeta + c, sb);
+  }
+}
+
+// ------------------------------------------------------------------------ L2 normalise
+// y = x / ||x||  (fp32 in, fp32 out, optional bf16 copy); one warp per row.
+__global__ void __launch_bounds__(128)
+l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ inv_norm, int rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = x[static_cast<long long>(r) * C + c];
+    s += v * v;
+  }
+  const float inv = 1.f / sqrtf(warp_sum(s));
+  for (int c = lane; c < C; c += 32) y[static_cast<long long>(r) * C + c] = x[static_cast<long long>(r) * C + c] * inv;
+  if (lane == 0) inv_norm[r] = inv;
+}
+// dx = (dy - y * (y . dy)) * inv_norm, written as bf16 (it feeds the projection dgrad/wgrad GEMMs).
+__global__ void __launch_bounds__(128)
+l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm,
+                  __nv_bfloat16* __restrict__ dx, int rows, int C, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += dy[static_cast<long long>(r) * C + c] * y[static_cast<long long>(r) * C + c];
+  s = warp_sum(s);
+  const float inv = inv_norm[r] * scale;
+  for (int c = lane; c < C; c += 32) {
+    const long long i = static_cast<long long>(r) * C + c;
+    dx[i] = __float2bfloat16((dy[i] - y[i] * s) * inv);
+  }
+}
+
+// ------------------------------------------------------------------------- column sums
+// out[c] += sum_r x[r, c]   (bias gradients).  grid.x covers column chunks of 256, grid.y splits rows.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int C,
+              float scale) {
+  __shared__ float part[8][256];
+  const int col8 = threadIdx.x & 31;        // 32 lanes x 8 columns = 256 columns
+  const int rl = threadIdx.x >> 5;          // 8 row lanes
+  const int c0 = blockIdx.x * 256 + col8 * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < C) {
+    for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + r * ld + c0), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[rl][col8 * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][threadIdx.x];
+    atomicAdd(out + c, s * scale);
+  }
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 casts
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *reinterpret_cast<uint4*>(dst + i) = pack8(f);
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+
+}  // namespace xp
+
+using namespace xp;
+
+extern "C" int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMap* ymap,
+                                const float* gamma, const float* beta, float* mean, float* rstd, int64_t rows,
+                                int32_t C, float eps, void* stream) {
+  if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_fwd: C must be a multiple of 8 and <= 1024");
+  if (rows <= 0) return 0;
+  ln_fwd_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), to_dev(*xmap), static_cast<__nv_bfloat16*>(y), to_dev(*ymap), gamma, beta,
+      mean, rstd, rows, C, eps);
+  XP_CHECK_LAUNCH("ln_fwd_kernel");
+  return 0;
+}
+
+extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const void* x, const XpRowMap* xmap,
+                                const float* gamma, const float* mean, const float* rstd, const void* dres,
+                                const XpRowMap* drmap, void* dx, const XpRowMap* dxmap, float* dgamma, float* dbeta,
+                                int64_t rows, int32_t C, void* stream) {
+  if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_bwd: C must be a multiple of 8 and <= 1024");
+  if (rows <= 0) return 0;
+  long long want = (rows + LNB_WARPS - 1) / LNB_WARPS;
+  const int grid = static_cast<int>(want < 4LL * sm_count() ? want : 4LL * sm_count());
+  const size_t smem = (static_cast<size_t>(LNB_WARPS) * 2 + 1) * C * sizeof(float);
+  XpRowMap none = {0, 0, 0, nullptr};
+  const int nv = (C / 8 + 31) / 32;
+#define XP_LNB_LAUNCH(NV)                                                                                           \
+  do {                                                                                                              \
+    static bool attr = false;                                                                                       \
+    if (!attr) {                                                                                                    \
+      XP_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                         (LNB_WARPS * 2 + 1) * 1024 * 4));                                          \
+      attr = true;                                                                                                  \
+    }                                                                                                               \
+    ln_bwd_kernel<NV><<<grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                           \
+        static_cast<const __nv_bfloat16*>(dy), to_dev(*dymap), static_cast<const __nv_bfloat16*>(x), to_dev(*xmap), \
+        gamma, mean, rstd, static_cast<const __nv_bfloat16*>(dres), to_dev(drmap ? *drmap : none),                  \
+        static_cast<__nv_bfloat16*>(dx), to_dev(*dxmap), dgamma, dbeta, rows, C);                                   \
+  } while (0)
+  if (nv == 1) XP_LNB_LAUNCH(1);
+  else if (nv == 2) XP_LNB_LAUNCH(2);
+  else if (nv == 3) XP_LNB_LAUNCH(3);
+  else XP_LNB_LAUNCH(4);
+#undef XP_LNB_LAUNCH
+  XP_CHECK_LAUNCH("ln_bwd_kernel");
+  return 0;
+}
+
+extern "C" int xp_l2norm_fwd(const float* x, float* y, float* inv_norm, int32_t rows, int32_t C, void* stream) {
+  if (rows <= 0) return 0;
+  l2norm_fwd_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, y, inv_norm, rows, C);
+  XP_CHECK_LAUNCH("l2norm_fwd_kernel");
+  return 0;
+}
+
+extern "C" int xp_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, void* dx_bf16, int32_t rows,
+                             int32_t C, float scale, void* stream) {
+  if (rows <= 0) return 0;
+  l2norm_bwd_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, y, inv_norm, static_cast<__nv_bfloat16*>(dx_bf16), rows, C, scale);
+  XP_CHECK_LAUNCH("l2norm_bwd_kernel");
+  return 0;
+}
+
+extern "C" int xp_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int32_t C, float scale,
+                              void* stream) {
+  if (C % 8 || ld % 8) return fail("xp_colsum_bf16: C and ld must be multiples of 8");
+  if (rows <= 0) return 0;
+  const int gx = (C + 255) / 256;
+  long long gy = (rows + 63) / 64;
+  const long long cap = (4LL * sm_count() + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  colsum_kernel<<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ld, out, rows, C, scale);
+  XP_CHECK_LAUNCH("colsum_kernel");
+  return 0;
+}
+
+extern "C" int xp_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    return fail("xp_cast_f32_bf16: pointers must be 16-byte aligned");
+  const long long blocks = (n + 2047) / 2048;
+  cast_f32_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n);
+  XP_CHECK_LAUNCH("cast_f32_bf16_kernel");
+  return 0;
+}

@@ -1,0 +1,597 @@
+"""B200-native CLIP-ViP dual encoder (video tower with video-proxy tokens + CLIP text tower).
+
+Drop-in for the reference's `CLIPModel` on the VidCLIP path (CLIP-ViP/src/modeling/CLIP_ViP.py): the
+module tree below exists only to hold parameters under the reference's exact `state_dict()` names
+(`vision_model.pre_layrnorm` spelling included, q/k/v kept as separate parameters), so
+released checkpoints, `named_parameters()`-driven weight-decay groups and `load_state_dict_with_mismatch`
+work unchanged.  None of these nn.Modules' own forward() is ever called: forward and backward run in one
+`torch.autograd.Function` that drives the hand-written sm_100a kernels through the C ABI (xpretrain_b200.ops).
+There is no eager / CPU fallback.
+
+Reference call stack replaced:
+  CLIPModel.forward            CLIP_ViP.py:1089-1172
+  CLIPVisionTransformer.forward :861-903, CLIPVisionViPEmbeddings.forward :168-197
+  CLIPTextTransformer.forward  :726-786, CLIPTextEmbeddings.forward :210-227
+  CLIPEncoderLayer.forward     :445-460, CLIPAttention.forward2 :332-381 / .forward :266-330, CLIPMLP.forward :392-396
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+@dataclass
+class TowerConfig:
+    hidden_size: int
+    num_attention_heads: int
+    num_hidden_layers: int
+    intermediate_size: int
+
+
+@dataclass
+class ClipVipConfig:
+    """openai/clip-vit-base-patch16 hyper-parameters + `vision_additional_config` (VidCLIP.py:11-27)."""
+
+    vision: TowerConfig = field(default_factory=lambda: TowerConfig(768, 12, 12, 3072))
+    text: TowerConfig = field(default_factory=lambda: TowerConfig(512, 8, 12, 2048))
+    image_size: int = 224
+    patch_size: int = 16
+    projection_dim: int = 512
+    vocab_size: int = 49408
+    max_position_embeddings: int = 77
+    layer_norm_eps: float = 1e-5
+    temporal_size: int = 12
+    if_use_temporal_embed: int = 1
+    add_cls_num: int = 3
+    logit_scale_init_value: float = 4.60
+
+    @property
+    def num_patches(self) -> int:
+        return (self.image_size // self.patch_size) ** 2
+
+
+# ----------------------------------------------------------------------- parameter containers
+class _Attention(nn.Module):
+    def __init__(self, width):
+        super().__init__()
+        self.k_proj = nn.Linear(width, width)
+        self.v_proj = nn.Linear(width, width)
+        self.q_proj = nn.Linear(width, width)
+        self.out_proj = nn.Linear(width, width)
+
+
+class _MLP(nn.Module):
+    def __init__(self, width, inner):
+        super().__init__()
+        self.fc1 = nn.Linear(width, inner)
+        self.fc2 = nn.Linear(inner, width)
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, tc: TowerConfig, eps):
+        super().__init__()
+        self.self_attn = _Attention(tc.hidden_size)
+        self.layer_norm1 = nn.LayerNorm(tc.hidden_size, eps=eps)
+        self.mlp = _MLP(tc.hidden_size, tc.intermediate_size)
+        self.layer_norm2 = nn.LayerNorm(tc.hidden_size, eps=eps)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, tc: TowerConfig, eps):
+        super().__init__()
+        self.layers = nn.ModuleList([_EncoderLayer(tc, eps) for _ in range(tc.num_hidden_layers)])
+
+
+class _VisionViPEmbeddings(nn.Module):
+    def __init__(self, cfg: ClipVipConfig):
+        super().__init__()
+        w = cfg.vision.hidden_size
+        self.added_cls = nn.Parameter(torch.randn(cfg.add_cls_num, w))
+        self.class_embedding = nn.Parameter(torch.randn(w))
+        self.patch_embedding = nn.Conv2d(3, w, kernel_size=cfg.patch_size, stride=cfg.patch_size, bias=False)
+        self.position_embedding = nn.Embedding(cfg.num_patches + 1, w)
+        self.register_buffer("position_ids", torch.arange(cfg.num_patches + 1).expand((1, -1)))
+        if cfg.if_use_temporal_embed:
+            self.temporal_embedding = nn.Parameter(torch.zeros(1, cfg.temporal_size, w))
+
+
+class _VisionTransformer(nn.Module):
+    def __init__(self, cfg: ClipVipConfig):
+        super().__init__()
+        self.embeddings = _VisionViPEmbeddings(cfg)
+        self.pre_layrnorm = nn.LayerNorm(cfg.vision.hidden_size, eps=cfg.layer_norm_eps)  # sic (reference spelling)
+        self.encoder = _Encoder(cfg.vision, cfg.layer_norm_eps)
+        self.post_layernorm = nn.LayerNorm(cfg.vision.hidden_size, eps=cfg.layer_norm_eps)
+
+
+class _TextEmbeddings(nn.Module):
+    def __init__(self, cfg: ClipVipConfig):
+        super().__init__()
+        self.token_embedding = nn.Embedding(cfg.vocab_size, cfg.text.hidden_size)
+        self.position_embedding = nn.Embedding(cfg.max_position_embeddings, cfg.text.hidden_size)
+        self.register_buffer("position_ids", torch.arange(cfg.max_position_embeddings).expand((1, -1)))
+
+
+class _TextTransformer(nn.Module):
+    def __init__(self, cfg: ClipVipConfig):
+        super().__init__()
+        self.embeddings = _TextEmbeddings(cfg)
+        self.encoder = _Encoder(cfg.text, cfg.layer_norm_eps)
+        self.final_layer_norm = nn.LayerNorm(cfg.text.hidden_size, eps=cfg.layer_norm_eps)
+
+
+def _tower_param_list(tower_prefix: str, n_layers: int) -> List[str]:
+    names = []
+    for i in range(n_layers):
+        p = f"{tower_prefix}.encoder.layers.{i}."
+        for lin in ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.out_proj", "mlp.fc1", "mlp.fc2"):
+            names += [p + lin + ".weight", p + lin + ".bias"]
+        for ln in ("layer_norm1", "layer_norm2"):
+            names += [p + ln + ".weight", p + ln + ".bias"]
+    return names
+
+
+class CLIPModel(nn.Module):
+    """Same constructor argument style, attribute names and output keys as the reference CLIPModel."""
+
+    def __init__(self, config: ClipVipConfig):
+        super().__init__()
+        self.config = config
+        self.vision_model = _VisionTransformer(config)
+        self.text_model = _TextTransformer(config)
+        self.visual_projection = nn.Linear(config.vision.hidden_size, config.projection_dim, bias=False)
+        self.text_projection = nn.Linear(config.text.hidden_size, config.projection_dim, bias=False)
+        self.logit_scale = nn.Parameter(torch.ones([]) * config.logit_scale_init_value)
+        self._init_weights()
+        self._packs: Dict[str, "_WeightPack"] = {}
+        # fixed parameter order handed to the autograd.Function (position_ids buffers excluded)
+        self._pnames = [n for n, _ in self.named_parameters() if n != "logit_scale"]
+
+    @torch.no_grad()
+    def _init_weights(self):
+        """CLIPPreTrainedModel._init_weights, CLIP_ViP.py:481-522 (initializer_factor 1, initializer_range 0.02)."""
+        cfg = self.config
+        te = self.text_model.embeddings
+        te.token_embedding.weight.normal_(0.0, 0.02)
+        te.position_embedding.weight.normal_(0.0, 0.02)
+        ve = self.vision_model.embeddings
+        ve.class_embedding.normal_(0.0, cfg.vision.hidden_size ** -0.5)
+        ve.patch_embedding.weight.normal_(0.0, 0.02)
+        ve.position_embedding.weight.normal_(0.0, 0.02)
+        for tower, tc in ((self.vision_model, cfg.vision), (self.text_model, cfg.text)):
+            in_std = tc.hidden_size ** -0.5 * (2 * tc.num_hidden_layers) ** -0.5
+            for layer in tower.encoder.layers:
+                for lin in (layer.self_attn.q_proj, layer.self_attn.k_proj, layer.self_attn.v_proj):
+                    lin.weight.normal_(0.0, in_std)
+                layer.self_attn.out_proj.weight.normal_(0.0, tc.hidden_size ** -0.5)
+                layer.mlp.fc1.weight.normal_(0.0, (2 * tc.hidden_size) ** -0.5)
+                layer.mlp.fc2.weight.normal_(0.0, in_std)
+        self.text_projection.weight.normal_(0.0, cfg.text.hidden_size ** -0.5)
+        self.visual_projection.weight.normal_(0.0, cfg.vision.hidden_size ** -0.5)
+        for m in self.modules():
+            if isinstance(m, nn.LayerNorm):
+                m.bias.zero_()
+                m.weight.fill_(1.0)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                m.bias.zero_()
+
+    # ------------------------------------------------------------------------------ public API
+    def forward(self, input_ids=None, pixel_values=None, attention_mask=None, return_loss=False, **_unused):
+        """CLIPModel.forward, CLIP_ViP.py:1089-1172 (return_loss is accepted and ignored, as VidCLIP passes False)."""
+        image_embeds, text_embeds = _run(self, pixel_values, input_ids, attention_mask)
+        return {"image_embeds": image_embeds, "text_embeds": text_embeds}
+
+    def get_image_features(self, pixel_values=None, if_norm=None, **_unused):
+        """CLIP_ViP.py:1043-1085: projected (and, if if_norm, L2-normalised) video features."""
+        image_embeds, _ = _run(self, pixel_values, None, None, normalize=bool(if_norm))
+        return image_embeds
+
+    def get_text_features(self, input_ids=None, attention_mask=None, if_norm=None, **_unused):
+        """CLIP_ViP.py:992-1041."""
+        _, text_embeds = _run(self, None, input_ids, attention_mask, normalize=bool(if_norm))
+        return text_embeds
+
+
+# -------------------------------------------------------------------- bf16 compute copies
+class _WeightPack:
+    """bf16 compute copies of one tower's GEMM weights with q/k/v fused to [3C, C]; refreshed from the fp32
+    master parameters whenever their version counters move (i.e. after an optimizer step)."""
+
+    def __init__(self, layers, device):
+        L = len(layers)
+        C_ = layers[0].self_attn.q_proj.weight.shape[0]
+        I = layers[0].mlp.fc1.weight.shape[0]
+        self.C, self.I, self.L = C_, I, L
+        self.wqkv = torch.empty(L, 3 * C_, C_, dtype=bf16, device=device)
+        self.wo = torch.empty(L, C_, C_, dtype=bf16, device=device)
+        self.w1 = torch.empty(L, I, C_, dtype=bf16, device=device)
+        self.w2 = torch.empty(L, C_, I, dtype=bf16, device=device)
+        self.bqkv = torch.empty(L, 3 * C_, dtype=f32, device=device)
+        self.version = None
+
+    def refresh(self, layers):
+        ver = tuple(p._version for layer in layers for p in layer.parameters())
+        if ver == self.version:
+            return
+        C_ = self.C
+        for i, layer in enumerate(layers):
+            a = layer.self_attn
+            for j, lin in enumerate((a.q_proj, a.k_proj, a.v_proj)):
+                ops.cast_bf16(lin.weight.detach(), self.wqkv[i], dst_offset=j * C_ * C_)
+                self.bqkv[i, j * C_:(j + 1) * C_].copy_(lin.bias.detach())
+            ops.cast_bf16(a.out_proj.weight.detach(), self.wo[i])
+            ops.cast_bf16(layer.mlp.fc1.weight.detach(), self.w1[i])
+            ops.cast_bf16(layer.mlp.fc2.weight.detach(), self.w2[i])
+        self.version = ver
+
+
+def _pack(model: CLIPModel, which: str) -> _WeightPack:
+    tower = model.vision_model if which == "vision" else model.text_model
+    layers = tower.encoder.layers
+    dev = layers[0].mlp.fc1.weight.device
+    pk = model._packs.get(which)
+    if pk is None or pk.wqkv.device != dev:
+        pk = _WeightPack(layers, dev)
+        model._packs[which] = pk
+    pk.refresh(layers)
+    return pk
+
+
+def _small_bf16(model: CLIPModel, name: str, p: torch.Tensor) -> torch.Tensor:
+    key = "small:" + name
+    ent = model._packs.get(key)
+    if ent is None or ent[0].device != p.device:
+        ent = [torch.empty(p.shape, dtype=bf16, device=p.device), None]
+        model._packs[key] = ent
+    if ent[1] != p._version:
+        ops.cast_bf16(p.detach().contiguous(), ent[0])
+        ent[1] = p._version
+    return ent[0]
+
+
+# --------------------------------------------------------------------------- encoder layers
+def _layer_fwd(x, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, rows: int, save: bool):
+    """One pre-LN residual block (CLIP_ViP.py:445-460).  x: [rows, C] bf16.  Returns (x_out, saved)."""
+    C_, I = pk.C, pk.I
+    dev = x.device
+    plain = ops.rowmap(C_)
+    mean1 = torch.empty(rows, dtype=f32, device=dev); rstd1 = torch.empty_like(mean1)
+    h = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.layernorm_fwd(x, plain, h, plain, layer.layer_norm1.weight, layer.layer_norm1.bias, mean1, rstd1, rows, C_, eps)
+    qkv = torch.empty(rows, 3 * C_, dtype=bf16, device=dev)
+    # q = (h Wq^T + bq) * head_dim**-0.5 : the scale multiplies the bias too (CLIP_ViP.py:341 / :269)
+    ops.linear_fwd(h, pk.wqkv[i], pk.bqkv[i], qkv, scale_cols=C_, col_scale=0.125)
+    a = torch.empty(rows, C_, dtype=bf16, device=dev)
+    att_saved = attn_fwd(qkv, a)
+    x1 = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.linear_fwd(a, pk.wo[i], layer.self_attn.out_proj.bias, x1, residual=x, ldr=C_)
+    mean2 = torch.empty(rows, dtype=f32, device=dev); rstd2 = torch.empty_like(mean2)
+    h2 = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.layernorm_fwd(x1, plain, h2, plain, layer.layer_norm2.weight, layer.layer_norm2.bias, mean2, rstd2, rows, C_, eps)
+    pre = torch.empty(rows, I, dtype=bf16, device=dev) if save else None
+    f1 = torch.empty(rows, I, dtype=bf16, device=dev)
+    ops.linear_fwd(h2, pk.w1[i], layer.mlp.fc1.bias, f1, act=_lib.ACT_QUICK_GELU, aux=pre, ld_aux=I)
+    out = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.linear_fwd(f1, pk.w2[i], layer.mlp.fc2.bias, out, residual=x1, ldr=C_)
+    saved = (x, mean1, rstd1, h, qkv, att_saved, a, x1, mean2, rstd2, h2, pre, f1) if save else None
+    return out, saved
+
+
+def _layer_bwd(dx, saved, layer, pk: _WeightPack, i: int, grads: Dict[str, torch.Tensor], prefix: str, attn_bwd,
+               rows: int):
+    """Backward of one block; dx [rows, C] bf16 is d(loss)/d(block output).  Returns d(block input)."""
+    (x, mean1, rstd1, h, qkv, att_saved, a, x1, mean2, rstd2, h2, pre, f1) = saved
+    C_, I = pk.C, pk.I
+    dev = dx.device
+    plain = ops.rowmap(C_)
+    g = lambda n: grads[prefix + n]  # noqa: E731
+    # ---- x_out = x1 + fc2(quick_gelu(fc1(LN2(x1))))
+    ops.linear_wgrad(dx, f1, g("mlp.fc2.weight"))
+    ops.colsum(dx, g("mlp.fc2.bias"))
+    dpre = torch.empty(rows, I, dtype=bf16, device=dev)
+    ops.linear_dgrad(dx, pk.w2[i], dpre, act=_lib.ACT_DQUICK_GELU, aux=pre, ld_aux=I)
+    ops.linear_wgrad(dpre, h2, g("mlp.fc1.weight"))
+    ops.colsum(dpre, g("mlp.fc1.bias"))
+    dh2 = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.linear_dgrad(dpre, pk.w1[i], dh2)
+    del dpre
+    dx1 = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.layernorm_bwd(dh2, plain, x1, plain, layer.layer_norm2.weight, mean2, rstd2, dx, plain, dx1, plain,
+                      g("layer_norm2.weight"), g("layer_norm2.bias"), rows, C_)
+    # ---- x1 = x + out_proj(attn(qkv(LN1(x))))
+    ops.linear_wgrad(dx1, a, g("self_attn.out_proj.weight"))
+    ops.colsum(dx1, g("self_attn.out_proj.bias"))
+    da = dh2  # reuse
+    ops.linear_dgrad(dx1, pk.wo[i], da)
+    dqkv = torch.empty(rows, 3 * C_, dtype=bf16, device=dev)
+    attn_bwd(qkv, a, da, att_saved, dqkv)
+    dwqkv = grads[prefix + "self_attn.qkv.weight"]
+    dbqkv = grads[prefix + "self_attn.qkv.bias"]
+    ops.linear_wgrad(dqkv, h, dwqkv)
+    ops.colsum(dqkv, dbqkv)
+    dh = da
+    ops.linear_dgrad(dqkv, pk.wqkv[i], dh)
+    del dqkv
+    dxin = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.layernorm_bwd(dh, plain, x, plain, layer.layer_norm1.weight, mean1, rstd1, dx1, plain, dxin, plain,
+                      g("layer_norm1.weight"), g("layer_norm1.bias"), rows, C_)
+    return dxin
+
+
+def _alloc_layer_grads(layer, prefix: str, grads: Dict[str, torch.Tensor], dev):
+    C_ = layer.self_attn.q_proj.weight.shape[0]
+    grads[prefix + "self_attn.qkv.weight"] = torch.zeros(3 * C_, C_, dtype=f32, device=dev)
+    grads[prefix + "self_attn.qkv.bias"] = torch.zeros(3 * C_, dtype=f32, device=dev)
+    for n, p in layer.named_parameters():
+        if ".q_proj." in n or ".k_proj." in n or ".v_proj." in n:
+            continue
+        grads[prefix + n] = torch.zeros(p.shape, dtype=f32, device=dev)
+
+
+def _finish_layer_grads(prefix: str, grads: Dict[str, torch.Tensor], C_: int):
+    w = grads.pop(prefix + "self_attn.qkv.weight")
+    b = grads.pop(prefix + "self_attn.qkv.bias")
+    for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+        grads[prefix + f"self_attn.{n}.weight"] = w[j * C_:(j + 1) * C_]
+        grads[prefix + f"self_attn.{n}.bias"] = b[j * C_:(j + 1) * C_]
+
+
+# ------------------------------------------------------------------------------ vision tower
+def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
+    cfg = model.config
+    vm = model.vision_model
+    emb = vm.embeddings
+    B, T = video.shape[0], video.shape[1]
+    C_, L, M = cfg.vision.hidden_size, cfg.num_patches, 1 + cfg.add_cls_num
+    H = cfg.vision.num_attention_heads
+    S = M + T * L
+    rows = B * S
+    dev = video.device
+    pk = _pack(model, "vision")
+    eps = cfg.layer_norm_eps
+    Kp = 3 * cfg.patch_size * cfg.patch_size
+
+    patches = torch.empty(B * T * L, Kp, dtype=bf16, device=dev)
+    ops.vip_patchify(video.contiguous(), patches, cfg.patch_size)
+    table = torch.empty(T * L, C_, dtype=bf16, device=dev)
+    x0 = torch.empty(rows, C_, dtype=bf16, device=dev)
+    temporal = emb.temporal_embedding if cfg.if_use_temporal_embed else None
+    ops.vip_embed_tables(emb.position_embedding.weight, temporal, emb.class_embedding, emb.added_cls, table, x0, B, T, L,
+                         M, C_, cfg.temporal_size)
+    wp = _small_bf16(model, "patch", emb.patch_embedding.weight).view(C_, Kp)
+    # conv-as-GEMM; epilogue adds the periodic [T*L, C] position+temporal table and writes past the M global rows
+    ops.gemm(patches, wp, x0, M=B * T * L, N=C_, K=Kp, lda=Kp, ldb=Kp, ldc=C_, residual=table, ldr=C_, r_group=T * L,
+             r_group_stride=0, c_group=T * L, c_group_stride=S * C_, c_offset=M * C_)
+    plain = ops.rowmap(C_)
+    # pre_layrnorm (CLIP_ViP.py:881) in two launches so that its statistics are stored compactly per half
+    # (patch rows / global rows), the layout its backward and the embedding backward consume
+    pmap = ops.rowmap(C_, group=T * L, group_stride=S * C_)
+    gmap = ops.rowmap(C_, group=M, group_stride=S * C_)
+    mean0p = torch.empty(B * T * L, dtype=f32, device=dev); rstd0p = torch.empty_like(mean0p)
+    mean0g = torch.empty(B * M, dtype=f32, device=dev); rstd0g = torch.empty_like(mean0g)
+    x = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ln0 = vm.pre_layrnorm
+    ops.layernorm_fwd(x0, pmap, x, pmap, ln0.weight, ln0.bias, mean0p, rstd0p, B * T * L, C_, eps, x_off=M * C_,
+                      y_off=M * C_)
+    ops.layernorm_fwd(x0, gmap, x, gmap, ln0.weight, ln0.bias, mean0g, rstd0g, B * M, C_, eps)
+
+    ws = ops.vip_attention_workspace(B, H, T, M, dev)
+
+    def attn_fwd(qkv, out):
+        lse = torch.empty(B, H, S, dtype=f32, device=dev)
+        ops.vip_attention_fwd(qkv, out, lse, ws, B, H, T, L, M, C_)
+        return lse
+
+    layer_saved = []
+    for i, layer in enumerate(vm.encoder.layers):
+        x, sv = _layer_fwd(x, layer, pk, i, eps, attn_fwd, rows, save)
+        layer_saved.append(sv)
+    # pooled = post_layernorm(last_hidden[:, 0])  (CLIP_ViP.py:891-893): CLS rows picked by the row map
+    cls_map = ops.rowmap(C_, group=1, group_stride=S * C_)
+    pooled = torch.empty(B, C_, dtype=bf16, device=dev)
+    meanp = torch.empty(B, dtype=f32, device=dev); rstdp = torch.empty_like(meanp)
+    ops.layernorm_fwd(x, cls_map, pooled, plain, vm.post_layernorm.weight, vm.post_layernorm.bias, meanp, rstdp, B, C_, eps)
+    wproj = _small_bf16(model, "vproj", model.visual_projection.weight)
+    proj = torch.empty(B, cfg.projection_dim, dtype=f32, device=dev)
+    ops.linear_fwd(pooled, wproj, None, proj, out_mode=_lib.OUT_F32)
+    saved = None
+    if save:
+        saved = SimpleNamespace(B=B, T=T, S=S, rows=rows, patches=patches, x0=x0, stats0=(mean0p, rstd0p, mean0g, rstd0g),
+                                layers=layer_saved, x_last=x, pooled=pooled, meanp=meanp, rstdp=rstdp, ws=ws)
+    return proj, saved
+
+
+def _vision_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str, torch.Tensor]):
+    """dproj_bf16 [B, proj] = gradient w.r.t. the un-normalised projection output."""
+    cfg = model.config
+    vm = model.vision_model
+    C_, L, M = cfg.vision.hidden_size, cfg.num_patches, 1 + cfg.add_cls_num
+    H = cfg.vision.num_attention_heads
+    B, T, S, rows = sv.B, sv.T, sv.S, sv.rows
+    dev = dproj_bf16.device
+    pk = _pack(model, "vision")
+    plain = ops.rowmap(C_)
+    wproj = _small_bf16(model, "vproj", model.visual_projection.weight)
+    ops.linear_wgrad(dproj_bf16, sv.pooled, grads["visual_projection.weight"])
+    dpooled = torch.empty(B, C_, dtype=bf16, device=dev)
+    ops.linear_dgrad(dproj_bf16, wproj, dpooled)
+    dx = torch.zeros(rows, C_, dtype=bf16, device=dev)  # only the CLS rows receive gradient from the head
+    cls_map = ops.rowmap(C_, group=1, group_stride=S * C_)
+    ops.layernorm_bwd(dpooled, plain, sv.x_last, cls_map, vm.post_layernorm.weight, sv.meanp, sv.rstdp, None, None, dx,
+                      cls_map, grads["vision_model.post_layernorm.weight"], grads["vision_model.post_layernorm.bias"], B, C_)
+
+    def attn_bwd(qkv, a, da, lse, dqkv):
+        ops.vip_attention_bwd(qkv, a, da, lse, dqkv, sv.ws, B, H, T, L, M, C_, 0.125)
+
+    for i in reversed(range(len(vm.encoder.layers))):
+        prefix = f"vision_model.encoder.layers.{i}."
+        dx = _layer_bwd(dx, sv.layers[i], vm.encoder.layers[i], pk, i, grads, prefix, attn_bwd, rows)
+        sv.layers[i] = None
+    # pre_layrnorm backward, written as two compact halves: patch rows [B, T*L, C] and global rows [B, M, C]
+    d_patch = torch.empty(B * T * L, C_, dtype=bf16, device=dev)
+    d_glob = torch.empty(B * M, C_, dtype=bf16, device=dev)
+    pmap = ops.rowmap(C_, group=T * L, group_stride=S * C_)
+    gmap = ops.rowmap(C_, group=M, group_stride=S * C_)
+    gw, gb = grads["vision_model.pre_layrnorm.weight"], grads["vision_model.pre_layrnorm.bias"]
+    mean0p, rstd0p, mean0g, rstd0g = sv.stats0
+    ops.layernorm_bwd(dx, pmap, sv.x0, pmap, vm.pre_layrnorm.weight, mean0p, rstd0p, None, None, d_patch, plain, gw, gb,
+                      B * T * L, C_, dy_off=M * C_, x_off=M * C_)
+    ops.layernorm_bwd(dx, gmap, sv.x0, gmap, vm.pre_layrnorm.weight, mean0g, rstd0g, None, None, d_glob, plain, gw, gb,
+                      B * M, C_)
+    emb = "vision_model.embeddings."
+    ops.vip_embed_bwd(d_patch, d_glob, grads[emb + "position_embedding.weight"],
+                      grads.get(emb + "temporal_embedding"), grads[emb + "class_embedding"], grads[emb + "added_cls"],
+                      B, T, L, M, C_, cfg.temporal_size)
+    Kp = 3 * cfg.patch_size * cfg.patch_size
+    ops.linear_wgrad(d_patch, sv.patches, grads[emb + "patch_embedding.weight"].view(C_, Kp))
+
+
+# -------------------------------------------------------------------------------- text tower
+def _text_fwd(model: CLIPModel, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], save: bool):
+    cfg = model.config
+    tm = model.text_model
+    B, Lt = input_ids.shape
+    C_, H = cfg.text.hidden_size, cfg.text.num_attention_heads
+    rows = B * Lt
+    dev = input_ids.device
+    pk = _pack(model, "text")
+    eps = cfg.layer_norm_eps
+    ids = input_ids.contiguous().to(torch.int64)
+    mask = attention_mask.contiguous().to(torch.int64) if attention_mask is not None else None
+    x = torch.empty(rows, C_, dtype=bf16, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.text_embed_fwd(ids, tm.embeddings.token_embedding.weight, tm.embeddings.position_embedding.weight, x, Lt, err)
+
+    def attn_fwd(qkv, out):
+        probs = torch.empty(B, H, Lt, Lt, dtype=f32, device=dev)
+        ops.text_attention_fwd(qkv, mask, out, probs, B, H, Lt, C_)
+        return probs
+
+    layer_saved = []
+    for i, layer in enumerate(tm.encoder.layers):
+        x, sv = _layer_fwd(x, layer, pk, i, eps, attn_fwd, rows, save)
+        layer_saved.append(sv)
+    # final_layer_norm is per-row, so it is applied to the pooled EOS row only (first argmax of the ids, :776)
+    eos = torch.empty(B, dtype=torch.int64, device=dev)
+    ops.eos_offsets(ids, eos, None, C_)
+    plain = ops.rowmap(C_)
+    emap = ops.rowmap(C_, offsets=eos)
+    pooled = torch.empty(B, C_, dtype=bf16, device=dev)
+    meanp = torch.empty(B, dtype=f32, device=dev); rstdp = torch.empty_like(meanp)
+    ops.layernorm_fwd(x, emap, pooled, plain, tm.final_layer_norm.weight, tm.final_layer_norm.bias, meanp, rstdp, B, C_, eps)
+    wproj = _small_bf16(model, "tproj", model.text_projection.weight)
+    proj = torch.empty(B, cfg.projection_dim, dtype=f32, device=dev)
+    ops.linear_fwd(pooled, wproj, None, proj, out_mode=_lib.OUT_F32)
+    saved = None
+    if save:
+        saved = SimpleNamespace(B=B, Lt=Lt, rows=rows, ids=ids, layers=layer_saved, x_last=x, eos=eos, pooled=pooled,
+                                meanp=meanp, rstdp=rstdp, err=err)
+    return proj, saved
+
+
+def _text_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str, torch.Tensor]):
+    cfg = model.config
+    tm = model.text_model
+    C_, H = cfg.text.hidden_size, cfg.text.num_attention_heads
+    B, Lt, rows = sv.B, sv.Lt, sv.rows
+    dev = dproj_bf16.device
+    pk = _pack(model, "text")
+    plain = ops.rowmap(C_)
+    wproj = _small_bf16(model, "tproj", model.text_projection.weight)
+    ops.linear_wgrad(dproj_bf16, sv.pooled, grads["text_projection.weight"])
+    dpooled = torch.empty(B, C_, dtype=bf16, device=dev)
+    ops.linear_dgrad(dproj_bf16, wproj, dpooled)
+    dx = torch.zeros(rows, C_, dtype=bf16, device=dev)
+    emap = ops.rowmap(C_, offsets=sv.eos)
+    ops.layernorm_bwd(dpooled, plain, sv.x_last, emap, tm.final_layer_norm.weight, sv.meanp, sv.rstdp, None, None, dx, emap,
+                      grads["text_model.final_layer_norm.weight"], grads["text_model.final_layer_norm.bias"], B, C_)
+
+    def attn_bwd(qkv, a, da, probs, dqkv):
+        ops.text_attention_bwd(qkv, da, probs, dqkv, B, H, Lt, C_, 0.125)
+
+    for i in reversed(range(len(tm.encoder.layers))):
+        prefix = f"text_model.encoder.layers.{i}."
+        dx = _layer_bwd(dx, sv.layers[i], tm.encoder.layers[i], pk, i, grads, prefix, attn_bwd, rows)
+        sv.layers[i] = None
+    ops.text_embed_bwd(sv.ids, dx, grads["text_model.embeddings.token_embedding.weight"],
+                       grads["text_model.embeddings.position_embedding.weight"], Lt, C_, cfg.vocab_size)
+
+
+# ------------------------------------------------------------------- the autograd.Function
+class _ClipVipFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: CLIPModel, video, input_ids, attention_mask, normalize, *params):
+        save = any(ctx.needs_input_grad[5:])
+        ctx.model = model
+        ctx.normalize = normalize
+        outs = []
+        ctx.vis = ctx.txt = None
+        dev = params[0].device
+        for which in ("vis", "txt"):
+            if which == "vis":
+                if video is None:
+                    outs.append(torch.empty(0, device=dev)); continue
+                proj, sv = _vision_fwd(model, video, save)
+            else:
+                if input_ids is None:
+                    outs.append(torch.empty(0, device=dev)); continue
+                proj, sv = _text_fwd(model, input_ids, attention_mask, save)
+            if normalize:
+                feat = torch.empty_like(proj)
+                inv = torch.empty(proj.shape[0], dtype=f32, device=dev)
+                ops.l2norm_fwd(proj, feat, inv)
+            else:
+                feat, inv = proj, None
+            if save:
+                sv.feat, sv.inv = feat, inv
+                setattr(ctx, which, sv)
+            outs.append(feat)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_vis, d_txt):
+        model: CLIPModel = ctx.model
+        dev = model.logit_scale.device
+        names = model._pnames
+        named = dict(model.named_parameters())
+        grads: Dict[str, torch.Tensor] = {}
+        C_v, C_t = model.config.vision.hidden_size, model.config.text.hidden_size
+        jobs = (("vision_model", ctx.vis, d_vis, "visual_projection.weight", _vision_bwd, C_v),
+                ("text_model", ctx.txt, d_txt, "text_projection.weight", _text_bwd, C_t))
+        for tower, sv, dfeat, proj_name, bwd, C_ in jobs:
+            if sv is None or dfeat is None:
+                continue
+            tw = getattr(model, tower)
+            for i, layer in enumerate(tw.encoder.layers):
+                _alloc_layer_grads(layer, f"{tower}.encoder.layers.{i}.", grads, dev)
+            for n in names:
+                if n.startswith(tower + ".") and ".encoder.layers." not in n:
+                    grads[n] = torch.zeros(named[n].shape, dtype=f32, device=dev)
+            grads[proj_name] = torch.zeros(named[proj_name].shape, dtype=f32, device=dev)
+            dproj = torch.empty(dfeat.shape, dtype=bf16, device=dev)
+            dfeat = dfeat.contiguous().to(f32)
+            if ctx.normalize:
+                ops.l2norm_bwd(dfeat, sv.feat, sv.inv, dproj)
+            else:
+                dproj.copy_(dfeat)
+            bwd(model, dproj, sv, grads)
+            for i in range(len(tw.encoder.layers)):
+                _finish_layer_grads(f"{tower}.encoder.layers.{i}.", grads, C_)
+        ctx.vis = ctx.txt = None
+        return (None, None, None, None, None) + tuple(grads.get(n) for n in names)
+
+
+def _run(model: CLIPModel, video, input_ids, attention_mask, normalize: bool = True):
+    if not model.logit_scale.is_cuda:
+        raise _lib.XpError("xpretrain_b200.CLIPModel must live on a CUDA (B200) device: there is no CPU path")
+    params = [p for n, p in model.named_parameters() if n != "logit_scale"]
+    vis, txt = _ClipVipFunction.apply(model, video, input_ids, attention_mask, normalize, *params)
+    return (vis if video is not None else None), (txt if input_ids is not None else None)

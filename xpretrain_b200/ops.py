@@ -1,0 +1,214 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch supplies device memory and the current stream only;
+every computation below runs in the hand-written sm_100a kernels of libxpretrain_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import XpGemm, XpRowMap, check, lib
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.XpError("xpretrain_b200 kernels need CUDA tensors (there is no CPU path)")
+    return t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(lib().xp_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().xp_launch_count_reset()
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int, ldc: int,
+         a_layout: int = 0, b_layout: int = 0, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, ldr: int = 0, aux: Optional[torch.Tensor] = None, ld_aux: int = 0,
+         act: int = _lib.ACT_NONE, out_mode: int = _lib.OUT_BF16, splits: int = 1, scale_cols: int = 0,
+         col_scale: float = 1.0, alpha: float = 1.0, c_group: int = 0, c_group_stride: int = 0, r_group: int = 0,
+         r_group_stride: int = 0, block_n: int = 0, a_offset: int = 0, b_offset: int = 0, c_offset: int = 0) -> None:
+    """out = epilogue(alpha * A @ B^T); offsets are in elements from the tensors' data pointers."""
+    assert a.dtype == bf16 and b.dtype == bf16
+    if bias is not None:
+        assert bias.dtype == f32 and bias.is_contiguous()
+    g = XpGemm()
+    g.a = _p(a) + a_offset * 2
+    g.b = _p(b) + b_offset * 2
+    g.c = _p(out) + c_offset * out.element_size()
+    g.bias = _p(bias)
+    g.residual = _p(residual)
+    g.aux = _p(aux)
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldc, g.ldr, g.ld_aux = lda, ldb, ldc, ldr, ld_aux
+    g.a_layout, g.b_layout, g.act, g.out = a_layout, b_layout, act, out_mode
+    g.splits, g.scale_cols, g.alpha, g.col_scale = splits, scale_cols, alpha, col_scale
+    g.c_group, g.c_group_stride, g.r_group, g.r_group_stride = c_group, c_group_stride, r_group, r_group_stride
+    g.block_n, g.max_ctas = block_n, 0
+    check(lib().xp_gemm(C.byref(g), _stream()), "xp_gemm")
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, **kw) -> None:
+    """out[M,N] = x[M,K] @ w[N,K]^T (+bias, epilogue)."""
+    M, K = x.shape
+    N = w.shape[0]
+    gemm(x, w, out, M=M, N=N, K=K, lda=x.stride(0), ldb=w.stride(0), ldc=out.stride(0), bias=bias, **kw)
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, **kw) -> None:
+    """dx[M,K] = dy[M,N] @ w[N,K]   (w in its nn.Linear layout: MN-major B operand)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    gemm(dy, w, dx, M=M, N=K, K=N, lda=dy.stride(0), ldb=w.stride(0), ldc=dx.stride(0), b_layout=1, **kw)
+
+
+def wgrad_plan(n_out: int, n_in: int, rows: int, sms: int = 148):
+    """(block_n, splits) for a weight-gradient GEMM: 256-wide tiles (96 B/clk/SM of operand traffic instead of
+    128) and the split-K factor that fills whole waves of the persistent grid."""
+    bn = 256 if n_in >= 256 else 128
+    tiles = ((n_out + 127) // 128) * ((n_in + bn - 1) // bn)
+    best, best_eff = 1, 0.0
+    for s in range(1, 17):
+        if s > 1 and rows // s < 1024:
+            break
+        total = tiles * s
+        eff = total / (((total + sms - 1) // sms) * sms)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return bn, best
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, alpha: float = 1.0) -> None:
+    """dw[N,K] += dy[rows,N]^T @ x[rows,K]  (fp32 atomics; both operands MN-major, split-K over the rows)."""
+    rows, N = dy.shape
+    K = x.shape[1]
+    assert dw.dtype == f32
+    bn, splits = wgrad_plan(N, K, rows)
+    gemm(dy, x, dw, M=N, N=K, K=rows, lda=dy.stride(0), ldb=x.stride(0), ldc=dw.stride(0), a_layout=1, b_layout=1,
+         out_mode=_lib.OUT_F32_ATOMIC, splits=splits, block_n=bn, alpha=alpha)
+
+
+# ------------------------------------------------------------------------------------ row kernels
+def rowmap(ld: int, group: int = 0, group_stride: int = 0, offsets: Optional[torch.Tensor] = None) -> XpRowMap:
+    m = XpRowMap()
+    m.group, m.group_stride, m.ld, m.offsets = group, group_stride, ld, _p(offsets)
+    return m
+
+
+def layernorm_fwd(x, xmap, y, ymap, gamma, beta, mean, rstd, rows: int, C_: int, eps: float, x_off=0, y_off=0):
+    check(lib().xp_layernorm_fwd(_p(x) + x_off * 2, C.byref(xmap), _p(y) + y_off * 2, C.byref(ymap), _p(gamma), _p(beta),
+                                 _p(mean), _p(rstd), rows, C_, eps, _stream()), "xp_layernorm_fwd")
+
+
+def layernorm_bwd(dy, dymap, x, xmap, gamma, mean, rstd, dres, drmap, dx, dxmap, dgamma, dbeta, rows: int, C_: int,
+                  dy_off=0, x_off=0, dres_off=0, dx_off=0):
+    check(lib().xp_layernorm_bwd(_p(dy) + dy_off * 2, C.byref(dymap), _p(x) + x_off * 2, C.byref(xmap), _p(gamma),
+                                 _p(mean), _p(rstd), (_p(dres) + dres_off * 2) if dres is not None else None,
+                                 C.byref(drmap) if drmap is not None else None, _p(dx) + dx_off * 2, C.byref(dxmap),
+                                 _p(dgamma), _p(dbeta), rows, C_, _stream()), "xp_layernorm_bwd")
+
+
+def l2norm_fwd(x, y, inv_norm):
+    rows, C_ = x.shape
+    check(lib().xp_l2norm_fwd(_p(x), _p(y), _p(inv_norm), rows, C_, _stream()), "xp_l2norm_fwd")
+
+
+def l2norm_bwd(dy, y, inv_norm, dx_bf16, scale: float = 1.0):
+    rows, C_ = y.shape
+    check(lib().xp_l2norm_bwd(_p(dy), _p(y), _p(inv_norm), _p(dx_bf16), rows, C_, scale, _stream()), "xp_l2norm_bwd")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+    rows, C_ = x.shape
+    check(lib().xp_colsum_bf16(_p(x), x.stride(0), _p(out), rows, C_, scale, _stream()), "xp_colsum_bf16")
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor, dst_offset: int = 0):
+    assert src.dtype == f32 and dst.dtype == bf16 and src.is_contiguous()
+    check(lib().xp_cast_f32_bf16(_p(src), _p(dst) + dst_offset * 2, src.numel(), _stream()), "xp_cast_f32_bf16")
+
+
+# ------------------------------------------------------------------------------------- embeddings
+_DT = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16}
+
+
+def vip_patchify(video: torch.Tensor, patches: torch.Tensor, patch: int):
+    frames = video.numel() // (3 * video.shape[-2] * video.shape[-1])
+    check(lib().xp_vip_patchify(_p(video), _DT[video.dtype], _p(patches), frames, video.shape[-2], video.shape[-1], patch,
+                                _stream()), "xp_vip_patchify")
+
+
+def vip_embed_tables(pos, temporal, cls, added, table, x, B, T, L, M, C_, temporal_size):
+    check(lib().xp_vip_embed_tables(_p(pos), _p(temporal), _p(cls), _p(added), _p(table), _p(x), B, T, L, M, C_,
+                                    temporal_size, _stream()), "xp_vip_embed_tables")
+
+
+def vip_embed_bwd(d_patch, d_global, d_pos, d_temporal, d_cls, d_added, B, T, L, M, C_, temporal_size):
+    check(lib().xp_vip_embed_bwd(_p(d_patch), _p(d_global), _p(d_pos), _p(d_temporal), _p(d_cls), _p(d_added), B, T, L, M,
+                                 C_, temporal_size, _stream()), "xp_vip_embed_bwd")
+
+
+def text_embed_fwd(ids, tok, pos, x, Lt, err_flag):
+    rows = ids.numel()
+    check(lib().xp_text_embed_fwd(_p(ids), _p(tok), _p(pos), _p(x), rows, Lt, tok.shape[1], tok.shape[0], _p(err_flag),
+                                  _stream()), "xp_text_embed_fwd")
+
+
+def text_embed_bwd(ids, dx, d_tok, d_pos, Lt, C_, vocab):
+    check(lib().xp_text_embed_bwd(_p(ids), _p(dx), _p(d_tok), _p(d_pos), ids.numel(), Lt, C_, vocab, _stream()),
+          "xp_text_embed_bwd")
+
+
+def eos_offsets(ids, offsets, index, C_):
+    B, Lt = ids.shape
+    check(lib().xp_eos_offsets(_p(ids), _p(offsets), _p(index), B, Lt, C_, _stream()), "xp_eos_offsets")
+
+
+# -------------------------------------------------------------------------------------- attention
+def vip_attention_workspace(B, H, T, M, device) -> torch.Tensor:
+    n = int(lib().xp_vip_attention_workspace_bytes(B, H, T, M))
+    return torch.empty(n // 4, dtype=f32, device=device)
+
+
+def vip_attention_fwd(qkv, out, lse, ws, B, H, T, L, M, C_):
+    check(lib().xp_vip_attention_fwd(_p(qkv), _p(out), _p(lse), _p(ws), B, H, T, L, M, C_, _stream()),
+          "xp_vip_attention_fwd")
+
+
+def vip_attention_bwd(qkv, out, dout, lse, dqkv, ws, B, H, T, L, M, C_, q_scale):
+    check(lib().xp_vip_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(ws), B, H, T, L, M, C_, q_scale,
+                                     _stream()), "xp_vip_attention_bwd")
+
+
+def text_attention_fwd(qkv, mask, out, probs, B, H, Lt, C_):
+    check(lib().xp_text_attention_fwd(_p(qkv), _p(mask), _p(out), _p(probs), B, H, Lt, C_, _stream()),
+          "xp_text_attention_fwd")
+
+
+def text_attention_bwd(qkv, dout, probs, dqkv, B, H, Lt, C_, q_scale):
+    check(lib().xp_text_attention_bwd(_p(qkv), _p(dout), _p(probs), _p(dqkv), B, H, Lt, C_, q_scale, _stream()),
+          "xp_text_attention_bwd")
+
+
+# -------------------------------------------------------------------------------------------- NCE
+def nce_split(x, x3, hi, pattern: int):
+    rows, d = x.shape
+    check(lib().xp_nce_split(_p(x), _p(x3), _p(hi), rows, d, pattern, _stream()), "xp_nce_split")
+
+
+def nce_softmax_grad(z, logit_scale, lse_r, lse_c, g_scaled, loss, d_logit_scale):
+    N, ld = z.shape[0], z.stride(0)
+    check(lib().xp_nce_softmax_grad(_p(z), _p(logit_scale), _p(lse_r), _p(lse_c), _p(g_scaled), _p(loss),
+                                    _p(d_logit_scale), N, ld, _stream()), "xp_nce_softmax_grad")

@@ -1,0 +1,142 @@
+"""In-batch video<->text InfoNCE with learnable temperature on the B200 kernels.
+
+API mirrors CLIP-ViP/src/optimization/loss.py: `build_loss_func(cfg)` (:326-328) returns a module whose
+`forward(vis_feat, text_feat, temp)` equals `NCELearnableTempLoss.forward` (:134-141):
+    logits = vis @ text.T * exp(temp);  loss = CE(logits, arange) + CE(logits.T, arange)      (sum, no 1/2)
+The logits GEMM and both gradient GEMMs run on the tcgen05 GEMM; softmax / loss / dL/dZ in nce.cu.
+`gather_nce_loss` is the fused multi-GPU form (embedding all-gather + loss, backward without a collective).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _nce_forward(vis: torch.Tensor, txt: torch.Tensor, temp: torch.Tensor):
+    """vis, txt: [N, d] fp32 (gathered).  Returns (loss[1], g_scaled[N, Np] bf16, vis_hi, txt_hi, dscale[1])."""
+    N, d = vis.shape
+    Np = _pad8(N)
+    dev = vis.device
+    a3 = torch.empty(N, 3 * d, dtype=bf16, device=dev)
+    b3 = torch.zeros(Np, 3 * d, dtype=bf16, device=dev) if Np != N else torch.empty(N, 3 * d, dtype=bf16, device=dev)
+    vh = torch.empty(N, d, dtype=bf16, device=dev)
+    th = torch.empty(N, d, dtype=bf16, device=dev)
+    ops.nce_split(vis.contiguous(), a3, vh, 0)
+    ops.nce_split(txt.contiguous(), b3, th, 1)
+    z = torch.empty(N, Np, dtype=f32, device=dev)
+    ops.gemm(a3, b3, z, M=N, N=Np, K=3 * d, lda=3 * d, ldb=3 * d, ldc=Np, out_mode=_lib.OUT_F32)
+    lse_r = torch.empty(N, dtype=f32, device=dev)
+    lse_c = torch.empty(N, dtype=f32, device=dev)
+    g = torch.empty(N, Np, dtype=bf16, device=dev)
+    loss = torch.empty(1, dtype=f32, device=dev)
+    dscale = torch.zeros(1, dtype=f32, device=dev)
+    ops.nce_softmax_grad(z, temp.detach().reshape(1).to(f32), lse_r, lse_c, g, loss, dscale)
+    return loss, g, vh, th, dscale
+
+
+def _nce_backward(g, vh, th, row0: int, nrows: int, scale: float):
+    """d_vis[row0:row0+nrows] = scale * (sG) T ;  d_txt[row0:row0+nrows] = scale * (sG)^T V   (fp32 [nrows, d])."""
+    N, d = vh.shape
+    Np = g.shape[1]
+    dev = g.device
+    d_vis = torch.empty(nrows, d, dtype=f32, device=dev)
+    d_txt = torch.empty(nrows, d, dtype=f32, device=dev)
+    # A = G rows (K-major), B = T stored [K=N, d] (MN-major)
+    ops.gemm(g, th, d_vis, M=nrows, N=d, K=N, lda=Np, ldb=d, ldc=d, b_layout=1, out_mode=_lib.OUT_F32, alpha=scale,
+             a_offset=row0 * Np)
+    # A = G^T: stored [K=N(i), M=N(j)] -> MN-major A, columns row0.. ; B = V stored [K=N, d]
+    ops.gemm(g, vh, d_txt, M=nrows, N=d, K=N, lda=Np, ldb=d, ldc=d, a_layout=1, b_layout=1, out_mode=_lib.OUT_F32,
+             alpha=scale, a_offset=row0)
+    return d_vis, d_txt
+
+
+class _NceFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vis, txt, temp):
+        loss, g, vh, th, dscale = _nce_forward(vis.to(f32), txt.to(f32), temp)
+        ctx.saved = (g, vh, th, dscale)
+        ctx.in_dtypes = (vis.dtype, txt.dtype, temp.dtype, temp.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        g, vh, th, dscale = ctx.saved
+        N = vh.shape[0]
+        d_vis, d_txt = _nce_backward(g, vh, th, 0, N, 1.0)
+        vd, td, pd, pshape = ctx.in_dtypes
+        return (d_vis * dloss).to(vd), (d_txt * dloss).to(td), (dscale * dloss).reshape(pshape).to(pd)
+
+
+class NCELearnableTempLoss(nn.Module):
+    """Drop-in for loss.py:126-141 (the cfg argument is accepted and unused, as in the reference)."""
+
+    def __init__(self, cfg=None):
+        super().__init__()
+
+    def forward(self, vis_feat, text_feat, temp):
+        return _NceFunction.apply(vis_feat, text_feat, temp)
+
+
+class _GatherNceFunction(torch.autograd.Function):
+    """allgather(vis), allgather(txt) -> loss, as one autograd node (run_pretrain.py:344-356).
+
+    Forward: ONE all-gather of the packed [2, b, d] local embeddings (NCCL over NVLink), then the loss.
+    Backward: every rank already holds all embeddings and computes the same scalar loss, so the local rows of
+    dV / dT are produced locally — no backward collective.  `grad_scale` = world size reproduces
+    all_reduce(SUM)-then-slice (LF-VILA/src/utils/dist.py:35-41), which a gradient-AVERAGING data-parallel
+    optimizer turns back into the true global-batch gradient."""
+
+    @staticmethod
+    def forward(ctx, vis, txt, temp, group, grad_scale):
+        import torch.distributed as dist
+
+        b, d = vis.shape
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        if world > 1:
+            local = torch.stack([vis.to(f32), txt.to(f32)]).contiguous()          # [2, b, d]
+            gathered = torch.empty(world, 2, b, d, dtype=f32, device=vis.device)
+            dist.all_gather_into_tensor(gathered, local, group=group)
+            V = gathered[:, 0].reshape(world * b, d)
+            T = gathered[:, 1].reshape(world * b, d)
+        else:
+            V, T = vis.to(f32), txt.to(f32)
+        loss, g, vh, th, dscale = _nce_forward(V.contiguous(), T.contiguous(), temp)
+        ctx.saved = (g, vh, th, dscale)
+        ctx.meta = (rank * b, b, float(world if grad_scale is None else grad_scale), vis.dtype, txt.dtype, temp.dtype,
+                    temp.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        g, vh, th, dscale = ctx.saved
+        row0, b, scale, vd, td, pd, pshape = ctx.meta
+        d_vis, d_txt = _nce_backward(g, vh, th, row0, b, scale)
+        return (d_vis * dloss).to(vd), (d_txt * dloss).to(td), (dscale * dloss).reshape(pshape).to(pd), None, None
+
+
+def gather_nce_loss(vis_feat, text_feat, temp, group=None, grad_scale: Optional[float] = None):
+    """Fused replacement for `hvd.allgather` x2 + `NCELearnableTempLoss` (run_pretrain.py:344-356)."""
+    return _GatherNceFunction.apply(vis_feat, text_feat, temp, group, grad_scale)
+
+
+_LOSSES = {"NCELearnableTempLoss": NCELearnableTempLoss}
+
+
+def build_loss_func(cfg):
+    """loss.py:326-328: `cfg.loss_name` selects the class."""
+    name = cfg["loss_name"] if isinstance(cfg, dict) else cfg.loss_name
+    if name not in _LOSSES:
+        raise NotImplementedError(f"loss {name!r} is outside the B200 hot path (SURVEY.md §8f lists it as 'next'); "
+                                  f"available: {sorted(_LOSSES)}")
+    return _LOSSES[name](cfg)
