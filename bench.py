@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the CLIP-ViP video-text hot path (BASELINE.json metric: video-text pairs/s, 12f x 224^2, 32 tok).
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+    VidCLIP forward (video tower + text tower)  ->  embedding all-gather + in-batch InfoNCE (learnable temperature)
+    ->  backward through both towers (all parameter gradients)  ->  (N > 1) data-parallel gradient averaging.
+Workload = BASELINE.json configs[1] per GPU: ViT-B/16, 12 frames x 224^2, 32 tokens, batch 64 per GPU, bf16 compute
+with fp32 master parameters / fp32 gradients, random-init weights of the reference's init statistics, synthetic data.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (N > 1: launched under torchrun, NCCL)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM (CUDA-event timed, max over ranks);
+`e2e` = the same through the public module API with pinned HOST buffers (prefetched H2D of every step's inputs and
+a D2H read of the loss inside the timed region); `roofline` = the tcgen05 GEMM kernel's achieved TFLOP/s over all of
+its launches in one step (CUDA events around each launch) against MEASURED_PEAKS.json; `cpu_baseline` = the oracle
+timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "video-text pairs/sec (12f x 224^2, 32 tok), CLIP-ViP ViT-B/16 fwd+InfoNCE+bwd"
+UNIT = "pairs/s"
+T_FRAMES, L_TOK, PER_GPU_BATCH = 12, 32, 64
+
+
+def flop_model():
+    from oracle import clipvip_oracle as O     # FLOP accounting only, never on the product path
+    return O.flops_per_pair(O.ClipVipCfg(), T_FRAMES, L_TOK)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))), "hbm_gbs": float(p["hbm_gbs"]),
+                "source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"}
+    return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback, sustained (of fallback)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, power, reasons = [], None, [], set()
+        for line in self.tmp.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax = float(parts[2]); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from xpretrain_b200 import ops
+    from xpretrain_b200.modeling import VidCLIP
+    from xpretrain_b200.optimization.loss import gather_nce_loss
+    from xpretrain_b200.utils import distributed as xdist
+
+    rank, local, world = xdist.init_from_env("nccl")
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, T, Lt = args.batch, T_FRAMES, L_TOK
+
+    add = SimpleNamespace(type="ViP", temporal_size=12, if_use_temporal_embed=1, logit_scale_init_value=4.60, add_cls_num=3)
+    torch.manual_seed(0)
+    model = VidCLIP(SimpleNamespace(clip_config="openai/clip-vit-base-patch16", clip_weights="",
+                                    clip_vision_additional_config=add))
+    with torch.no_grad():
+        model.clipmodel.vision_model.embeddings.temporal_embedding.normal_(0, 0.02)
+    model = model.to(dev)
+    params = [p for p in model.parameters()]
+
+    # synthetic inputs: pinned host copies for the e2e leg, device copies for the resident leg
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host = 2
+    host = []
+    for _ in range(n_host):
+        v = torch.randn(B, T, 3, 224, 224, generator=g).pin_memory()
+        ids = torch.randint(1, 49406, (B, Lt), generator=g)
+        ids[:, -1] = 49407
+        host.append((v, ids.pin_memory(), torch.ones(B, Lt, dtype=torch.long).pin_memory()))
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+
+    def step(video, ids, mask):
+        for p in params:
+            p.grad = None
+        out = model(video=video, text_input_ids=ids, text_input_mask=mask)
+        loss = gather_nce_loss(out["vis_features"], out["text_features"], model.clipmodel.logit_scale)
+        loss.backward()
+        xdist.average_gradients(params)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps between barrier+synchronize on both sides; CUDA-event time, max over ranks (ms per step)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for i in range(args.warmup):
+        step(*resident[i % n_host])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms_resident = timed(lambda i: step(*resident[i % n_host]), args.steps)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers -> prefetched H2D on a side stream (the reference's PrefetchLoader pattern,
+    #      dataloader.py:92-157) -> module API -> loss.item() (D2H) every step
+    copy_stream = torch.cuda.Stream()
+    slots = [None, None]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            slots[i % 2] = tuple(t.to(dev, non_blocking=True) for t in host[i % n_host])
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        return ev
+
+    last = {"loss": None}
+
+    def e2e_loop(steps):
+        ev = prefetch(0)
+        for i in range(steps):
+            torch.cuda.current_stream().wait_event(ev)
+            batch = slots[i % 2]
+            for t in batch:
+                t.record_stream(torch.cuda.current_stream())
+            if i + 1 < steps:
+                ev = prefetch(i + 1)
+            last["loss"] = float(step(*batch))            # .item(): device -> host read of the step's result
+
+    e2e_loop(2)                                            # warm the copy path
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms_t) / args.steps
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM): CUDA events around every launch of one step
+    roof = None
+    if rank == 0 or world > 1:
+        rec = []
+        ops.set_gemm_timer(rec)
+        step(*resident[0])
+        torch.cuda.synchronize()
+        ops.set_gemm_timer(None)
+        g_ms = sum(e0_.elapsed_time(e1_) for (_, e0_, e1_) in rec)
+        g_flops = sum(f for (f, _, _) in rec)
+        peaks = measured_peaks()
+        achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        roof = {"kernel": "xp::gemm_kernel (tcgen05 bf16, all launches of one step)", "bound": "tensor",
+                "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["source"],
+                "launches_per_step": len(rec), "gemm_ms_per_step": round(g_ms, 3),
+                "gemm_share_of_step": round(g_ms / ms_resident, 4)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fm = flop_model()
+    pairs = B * world
+    value = pairs / (ms_resident * 1e-3)
+    e2e_value = pairs / (ms_e2e * 1e-3)
+    peaks = measured_peaks()
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_resident, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"CLIP-ViP ViT-B/16, {T} frames x 224^2, {Lt} tok, batch {B}/GPU (BASELINE.json configs[1]"
+                               f"{'/[2]' if world > 1 else ''}); step = fwd + gather + InfoNCE + bwd"
+                               f"{' + DP grad all-reduce' if world > 1 else ''}",
+                   "global_batch": pairs, "frames": T, "tokens": Lt, "parallelism": f"dp{world}",
+                   "l2": "inputs (462 MB video + 40 GB activations per step) far exceed the 126 MB L2",
+                   "weights": "random init with the reference's init statistics, fp32 masters, bf16 compute copies"},
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 3),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": last["loss"]},
+        "gpu_launches": int(launches * world),
+        "clocks": clocks,
+        "roofline": roof,
+        "whole_step": {"flops_per_pair": fm["train"], "tflops_per_gpu": round(value / world * fm["train"] / 1e12, 1),
+                       "frac_of_peak": round(value / world * fm["train"] / 1e12 / peaks["tflops"], 4)},
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(steps=1, warmup=1, batch=args.cpu_batch)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------------- reference / CPU arm
+def cpu_step_fn(batch):
+    """The reference algorithm (oracle port of CLIP_ViP.py + loss.py) on the host: fwd + loss + bwd, fp32 eager."""
+    import torch
+    from oracle import clipvip_oracle as O
+    cfg = O.ClipVipCfg()
+    sd = O.init_state_dict(cfg, seed=0)
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    video, ids, mask = O.synthetic_batch(batch, T_FRAMES, L_TOK, cfg, seed=1234)
+
+    def fn():
+        for v in sd.values():
+            if v.is_floating_point():
+                v.grad = None
+        out = O.clip_vip_forward(sd, video, ids, mask, cfg)
+        loss = O.nce_learnable_temp_loss(out["vis_features"], out["text_features"], sd["logit_scale"])
+        loss.backward()
+        return float(loss)
+    return fn
+
+
+def cpu_baseline(steps, warmup, batch):
+    import torch
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    torch.set_num_threads(threads)
+    fn = cpu_step_fn(batch)
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(batch / dt, 3), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of batch {batch} x {T_FRAMES} frames x 224^2 + {L_TOK} tok, 12+12 layers, fp32 eager "
+                      f"fwd+loss+bwd (oracle/clipvip_oracle.py, pinned to the reference by tests/golden/make_golden.py)",
+            "seconds_per_step": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_baseline(steps=args.steps, warmup=args.warmup, batch=args.cpu_batch)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(base["seconds_per_step"] * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CLIP-ViP ViT-B/16, {T_FRAMES} frames x 224^2, {L_TOK} tok; each step a bounded sample "
+                                   f"of batch {args.cpu_batch} on the host CPU (the reference is pure PyTorch; its own "
+                                   f"CPU path = fp32 eager)", "global_batch": args.cpu_batch, "parallelism": "cpu"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE.json configs[1]: 64)")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="pairs per CPU-baseline step (bounded sample)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

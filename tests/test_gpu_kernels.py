@@ -169,7 +169,7 @@ def test_patchify_and_embed_tables(dev):
     from xpretrain_b200 import ops
     cfg = O.ClipVipCfg()
     B, T = 2, 5                                 # T != temporal_size -> linear interpolation of the table
-    sd = O.init_state_dict(O.ClipVipCfg(vision=O.TowerCfg(768, 12, 0, 3072), text=O.TowerCfg(512, 8, 0, 2048)), seed=3)
+    sd = O.init_state_dict(O.ClipVipCfg(vision=O.TowerCfg(768, 12, 1, 3072), text=O.TowerCfg(512, 8, 1, 2048)), seed=3)
     video = torch.randn(B, T, 3, 224, 224, generator=torch.Generator().manual_seed(4))
     want, (M, _, L) = O.vip_embeddings(sd, video, cfg)
     C, Kp, S = 768, 768, M + T * L

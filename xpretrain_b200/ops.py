@@ -57,7 +57,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.splits, g.scale_cols, g.alpha, g.col_scale = splits, scale_cols, alpha, col_scale
     g.c_group, g.c_group_stride, g.r_group, g.r_group_stride = c_group, c_group_stride, r_group, r_group_stride
     g.block_n, g.max_ctas = block_n, 0
-    check(lib().xp_gemm(C.byref(g), _stream()), "xp_gemm")
+    if _gemm_timer is None:
+        check(lib().xp_gemm(C.byref(g), _stream()), "xp_gemm")
+    else:  # bench.py's roofline leg: CUDA events on the launching stream around this launch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().xp_gemm(C.byref(g), _stream()), "xp_gemm")
+        e1.record()
+        _gemm_timer.append((2.0 * M * N * K, e0, e1))
+
+
+_gemm_timer = None
+
+
+def set_gemm_timer(records) -> None:
+    """records: a list receiving (flops, start_event, end_event) per GEMM launch, or None to switch timing off."""
+    global _gemm_timer
+    _gemm_timer = records
 
 
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, **kw) -> None:
