@@ -45,6 +45,50 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+typedef CUresult (*CtxGetCurrentFn)(CUcontext*);
+typedef CUresult (*CtxSetCurrentFn)(CUcontext);
+typedef CUresult (*PointerGetAttributeFn)(void*, CUpointer_attribute, CUdeviceptr);
+
+static void* driver_symbol(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return p;
+}
+
+int ensure_context(const void* device_ptr) {
+  static thread_local bool bound = false;
+  if (bound) return 0;
+  static CtxGetCurrentFn get_cur = reinterpret_cast<CtxGetCurrentFn>(driver_symbol("cuCtxGetCurrent"));
+  static CtxSetCurrentFn set_cur = reinterpret_cast<CtxSetCurrentFn>(driver_symbol("cuCtxSetCurrent"));
+  static PointerGetAttributeFn ptr_attr =
+      reinterpret_cast<PointerGetAttributeFn>(driver_symbol("cuPointerGetAttribute"));
+  if (!get_cur || !set_cur || !ptr_attr)
+    return fail("CUDA driver unavailable (no GPU): this library has no CPU path");
+  CUcontext cur = nullptr;
+  if (get_cur(&cur) == CUDA_SUCCESS && cur != nullptr) {
+    bound = true;
+    return 0;
+  }
+  if (device_ptr == nullptr) return fail("null device pointer");
+  CUcontext owner = nullptr;
+  if (ptr_attr(&owner, CU_POINTER_ATTRIBUTE_CONTEXT, reinterpret_cast<CUdeviceptr>(device_ptr)) == CUDA_SUCCESS &&
+      owner != nullptr) {
+    if (set_cur(owner) != CUDA_SUCCESS) return fail("cuCtxSetCurrent failed");
+  } else {
+    // pool / stream-ordered allocations report no owning context: fall back to the device ordinal
+    int ordinal = -1;
+    if (ptr_attr(&ordinal, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, reinterpret_cast<CUdeviceptr>(device_ptr)) !=
+            CUDA_SUCCESS ||
+        ordinal < 0)
+      return fail("cannot find the CUDA device of the first pointer argument (is it a device pointer?)");
+    if (cudaSetDevice(ordinal) != cudaSuccess) return fail("cudaSetDevice failed");
+  }
+  bound = true;
+  return 0;
+}
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride,
                       uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = encode_fn();

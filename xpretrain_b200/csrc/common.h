@@ -21,6 +21,16 @@ int sm_count();  // SMs of the current device (cached per device)
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride,
                       uint32_t box_inner, uint32_t box_outer);
 
+// Bind the CUDA context that owns `device_ptr` to the calling thread if the thread has none.  PyTorch runs
+// autograd backward on worker threads that may not have touched CUDA yet; this library links its own
+// (static) runtime, so without this a first call from such a thread would see "no current context" (or
+// silently use device 0 on a multi-GPU rank).
+int ensure_context(const void* device_ptr);
+#define XP_ENTER(ptr)                                   \
+  do {                                                  \
+    if (::xp::ensure_context(ptr) != 0) return -1;      \
+  } while (0)
+
 #define XP_CHECK_CUDA(expr)                                                                         \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \

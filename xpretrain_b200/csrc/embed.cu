@@ -230,6 +230,7 @@ using namespace xp;
 
 extern "C" int xp_vip_patchify(const void* video, int32_t dtype, void* patches_bf16, int64_t frames, int32_t H,
                                int32_t W, int32_t patch, void* stream) {
+  XP_ENTER(video);
   if (patch % 8 || W % patch || H % patch) return fail("xp_vip_patchify: patch must be a multiple of 8 dividing H and W");
   const long long total = frames * 3 * H * (W / 8);
   if (total <= 0) return 0;
@@ -251,6 +252,7 @@ extern "C" int xp_vip_patchify(const void* video, int32_t dtype, void* patches_b
 extern "C" int xp_vip_embed_tables(const float* pos, const float* temporal, const float* cls, const float* added,
                                    void* table_bf16, void* x_bf16, int32_t B, int32_t T, int32_t L, int32_t M,
                                    int32_t C, int32_t temporal_size, void* stream) {
+  XP_ENTER(pos);
   const long long S = static_cast<long long>(M) + static_cast<long long>(T) * L;
   const int grid = T * L + B * M;
   vip_embed_tables_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -263,6 +265,7 @@ extern "C" int xp_vip_embed_tables(const float* pos, const float* temporal, cons
 extern "C" int xp_vip_embed_bwd(const void* d_patch_bf16, const void* d_global_bf16, float* d_pos, float* d_temporal,
                                 float* d_cls, float* d_added, int32_t B, int32_t T, int32_t L, int32_t M, int32_t C,
                                 int32_t temporal_size, void* stream) {
+  XP_ENTER(d_patch_bf16);
   if (C % 8 || C > 1024) return fail("xp_vip_embed_bwd: C must be a multiple of 8 and <= 1024");
   const long long S = static_cast<long long>(M) + static_cast<long long>(T) * L;
   vip_embed_bwd_kernel<<<static_cast<unsigned>(S), 128, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -274,6 +277,7 @@ extern "C" int xp_vip_embed_bwd(const void* d_patch_bf16, const void* d_global_b
 
 extern "C" int xp_text_embed_fwd(const int64_t* ids, const float* tok, const float* pos, void* x_bf16, int32_t rows,
                                  int32_t Lt, int32_t C, int32_t vocab, int32_t* err_flag, void* stream) {
+  XP_ENTER(ids);
   if (C % 4) return fail("xp_text_embed_fwd: C must be a multiple of 4");
   if (rows <= 0) return 0;
   text_embed_fwd_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -284,6 +288,7 @@ extern "C" int xp_text_embed_fwd(const int64_t* ids, const float* tok, const flo
 
 extern "C" int xp_text_embed_bwd(const int64_t* ids, const void* dx_bf16, float* d_tok, float* d_pos, int32_t rows,
                                  int32_t Lt, int32_t C, int32_t vocab, void* stream) {
+  XP_ENTER(ids);
   if (rows <= 0) return 0;
   text_embed_bwd_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(ids), static_cast<const __nv_bfloat16*>(dx_bf16), d_tok, d_pos, Lt, C, vocab);
@@ -293,6 +298,7 @@ extern "C" int xp_text_embed_bwd(const int64_t* ids, const void* dx_bf16, float*
 
 extern "C" int xp_eos_offsets(const int64_t* ids, int64_t* offsets, int32_t* index, int32_t B, int32_t Lt, int32_t C,
                               void* stream) {
+  XP_ENTER(ids);
   if (B <= 0) return 0;
   eos_offsets_kernel<<<B, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(ids),
                                                                      reinterpret_cast<long long*>(offsets), index, Lt, C);

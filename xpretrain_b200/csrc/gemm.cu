@@ -32,6 +32,7 @@ struct GemmDev {
   int splits;
   int scale_cols;
   float alpha, col_scale;
+  int wide;                 // C / aux / residual rows are 32-byte aligned (ld % 16 == 0)
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes): 64-element atom stride, 8-k-row group stride
 };
 
@@ -51,6 +52,37 @@ __device__ __forceinline__ float act_gelu_erf_grad(float x) {
   float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
   float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+
+// 16 consecutive bf16 (32 bytes) of one row: one 256-bit access when the row segment is 32-byte aligned,
+// else two 128-bit accesses (the second only if those 8 columns exist).
+__device__ __forceinline__ void ld_bf16x16(const __nv_bfloat16* ptr, bool wide, bool second, uint32_t (&w)[8]) {
+  if (wide) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(ptr));
+  } else {
+    const uint4 a = *reinterpret_cast<const uint4*>(ptr);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = w[5] = w[6] = w[7] = 0u;
+    if (second) {
+      const uint4 b = *reinterpret_cast<const uint4*>(ptr + 8);
+      w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    }
+  }
+}
+__device__ __forceinline__ void st_bf16x16(__nv_bfloat16* ptr, bool wide, bool second, const float (&v)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  if (wide) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  } else {
+    *reinterpret_cast<uint4*>(ptr) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (second) *reinterpret_cast<uint4*>(ptr + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
 }
 
 template <int BN, int A_MN, int B_MN, int OUT>
@@ -190,6 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = ew >> 2;
     const int etid = threadIdx.x - 128;  // 0..255
     constexpr int CHUNKS = BN / 64;      // 32-column chunks per warp per tile
+    const bool wide = p.wide != 0;       // every bf16 row segment is 32-byte aligned -> 256-bit accesses
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -230,86 +263,85 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int nl = half * (BN / 2) + c * 32;  // column within the tile
         const int n0 = n_blk * BN + nl;
         if (row_ok && n0 < p.N) {
-          // issue the global reads of this chunk first so their latency overlaps
-          uint4 rres[4], raux[4];
+          // two groups of 16 columns: 32-byte global accesses (one full sector per lane) when `wide`
           const bool need_aux_in = (p.act == XP_ACT_DQUICK_GELU || p.act == XP_ACT_DGELU_ERF);
+          uint32_t rres[2][8], raux[2][8];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + g * 8;
+          for (int g = 0; g < 2; ++g) {  // issue this chunk's global reads first so their latency overlaps
+            const int n = n0 + g * 16;
             if (n < p.N) {
-              if (p.residual != nullptr) rres[g] = *reinterpret_cast<const uint4*>(p.residual + r_off + n);
-              if (need_aux_in) raux[g] = *reinterpret_cast<const uint4*>(p.aux + a_off + n);
+              const bool full = wide && (n + 16 <= p.N);
+              if (p.residual != nullptr) ld_bf16x16(p.residual + r_off + n, full, n + 8 < p.N, rres[g]);
+              if (need_aux_in) ld_bf16x16(p.aux + a_off + n, full, n + 8 < p.N, raux[g]);
             }
           }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + g * 8;
+          for (int g = 0; g < 2; ++g) {
+            const int n = n0 + g * 16;
             if (n < p.N) {
-              float v[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(sbias + nl + g * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(sbias + nl + g * 8 + 4);
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              const bool second = n + 8 < p.N;          // N % 8 == 0: a group holds 8 or 16 valid columns
+              const bool full = wide && (n + 16 <= p.N);
+              float v[16];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaf(__uint_as_float(r[g * 8 + i]), p.alpha, bb[i]);
+              for (int q = 0; q < 4; ++q) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + nl + g * 16 + q * 4);
+                v[q * 4 + 0] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 0]), p.alpha, b.x);
+                v[q * 4 + 1] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 1]), p.alpha, b.y);
+                v[q * 4 + 2] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 2]), p.alpha, b.z);
+                v[q * 4 + 3] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 3]), p.alpha, b.w);
+              }
               if (n < p.scale_cols) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] *= p.col_scale;
+                if (n + 8 < p.scale_cols) {
+#pragma unroll
+                  for (int i = 8; i < 16; ++i) v[i] *= p.col_scale;
+                }
               }
-              if (p.act == XP_ACT_QUICK_GELU || p.act == XP_ACT_GELU_ERF) {
-                if (p.aux != nullptr) {
-                  uint4 h;
-                  h.x = pack_bf16(v[0], v[1]); h.y = pack_bf16(v[2], v[3]);
-                  h.z = pack_bf16(v[4], v[5]); h.w = pack_bf16(v[6], v[7]);
-                  *reinterpret_cast<uint4*>(p.aux + a_off + n) = h;
+              if (p.act == XP_ACT_QUICK_GELU) {
+                if (p.aux != nullptr) st_bf16x16(p.aux + a_off + n, full, second, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = quick_gelu(v[i]);
+              } else if (p.act == XP_ACT_DQUICK_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  v[2 * i] *= quick_gelu_grad(bf16_lo(raux[g][i]));
+                  v[2 * i + 1] *= quick_gelu_grad(bf16_hi(raux[g][i]));
                 }
-                if (p.act == XP_ACT_QUICK_GELU) {
+              } else if (p.act == XP_ACT_GELU_ERF) {
+                if (p.aux != nullptr) st_bf16x16(p.aux + a_off + n, full, second, v);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
-                } else {
+                for (int i = 0; i < 16; ++i) v[i] = act_gelu_erf(v[i]);
+              } else if (p.act == XP_ACT_DGELU_ERF) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = act_gelu_erf(v[i]);
-                }
-              } else if (need_aux_in) {
-                const uint32_t hw[4] = {raux[g].x, raux[g].y, raux[g].z, raux[g].w};
-                if (p.act == XP_ACT_DQUICK_GELU) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    v[2 * i] *= quick_gelu_grad(bf16_lo(hw[i]));
-                    v[2 * i + 1] *= quick_gelu_grad(bf16_hi(hw[i]));
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    v[2 * i] *= act_gelu_erf_grad(bf16_lo(hw[i]));
-                    v[2 * i + 1] *= act_gelu_erf_grad(bf16_hi(hw[i]));
-                  }
+                for (int i = 0; i < 8; ++i) {
+                  v[2 * i] *= act_gelu_erf_grad(bf16_lo(raux[g][i]));
+                  v[2 * i + 1] *= act_gelu_erf_grad(bf16_hi(raux[g][i]));
                 }
               }
               if (p.residual != nullptr) {
-                const uint32_t qw[4] = {rres[g].x, rres[g].y, rres[g].z, rres[g].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  v[2 * i] += bf16_lo(qw[i]);
-                  v[2 * i + 1] += bf16_hi(qw[i]);
+                for (int i = 0; i < 8; ++i) {
+                  v[2 * i] += bf16_lo(rres[g][i]);
+                  v[2 * i + 1] += bf16_hi(rres[g][i]);
                 }
               }
               if (OUT == XP_OUT_BF16) {
-                uint4 o;
-                o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-                o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.c) + c_off + n) = o;
+                st_bf16x16(static_cast<__nv_bfloat16*>(p.c) + c_off + n, full, second, v);
               } else if (OUT == XP_OUT_F32) {
                 float* dst = static_cast<float*>(p.c) + c_off + n;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (q < 2 || second)
+                    *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
               } else {
                 float* dst = static_cast<float*>(p.c) + c_off + n;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]),
-                             "f"(v[2]), "f"(v[3])
-                             : "memory");
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]),
-                             "f"(v[6]), "f"(v[7])
-                             : "memory");
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (q < 2 || second)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(v[q * 4]),
+                                 "f"(v[q * 4 + 1]), "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3])
+                                 : "memory");
               }
             }
           }
@@ -382,6 +414,7 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return fail("xp_gemm: M, N, K must be positive");
   if (g->N % 8 != 0) return fail("xp_gemm: N must be a multiple of 8");
   if (!g->a || !g->b || !g->c) return fail("xp_gemm: null operand");
+  XP_ENTER(g->a);
   const int splits = g->splits <= 0 ? 1 : g->splits;
   if (splits > 1 && g->out != XP_OUT_F32_ATOMIC) return fail("xp_gemm: split-K requires XP_OUT_F32_ATOMIC");
   if ((g->act == XP_ACT_DQUICK_GELU || g->act == XP_ACT_DGELU_ERF) && !g->aux)
@@ -440,6 +473,11 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
   dev.scale_cols = g->scale_cols;
   dev.alpha = g->alpha;
   dev.col_scale = g->col_scale;
+  {
+    auto ok32 = [](const void* ptr, long long ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0); };
+    dev.wide = (g->out != XP_OUT_BF16 || ok32(g->c, g->ldc)) && ok32(g->aux, g->ld_aux) && ok32(g->residual, g->ldr) &&
+               (g->c_group_stride % 16 == 0) && (g->r_group_stride % 16 == 0);
+  }
   dev.mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : BK * 128;
   dev.mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024;
 

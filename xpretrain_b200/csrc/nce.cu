@@ -84,6 +84,7 @@ using namespace xp;
 
 extern "C" int xp_nce_split(const float* x, void* x3_bf16, void* hi_bf16, int32_t rows, int32_t d, int32_t pattern,
                             void* stream) {
+  XP_ENTER(x);
   if (rows <= 0) return 0;
   nce_split_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<__nv_bfloat16*>(x3_bf16), static_cast<__nv_bfloat16*>(hi_bf16), d, pattern);
@@ -94,6 +95,7 @@ extern "C" int xp_nce_split(const float* x, void* x3_bf16, void* hi_bf16, int32_
 extern "C" int xp_nce_softmax_grad(const float* z, const float* logit_scale, float* lse_rows, float* lse_cols,
                                    void* g_scaled_bf16, float* loss, float* d_logit_scale, int32_t N, int64_t ld,
                                    void* stream) {
+  XP_ENTER(z);
   if (N <= 0) return fail("xp_nce_softmax_grad: N must be positive");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   XP_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));

@@ -174,10 +174,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+// sigmoid(y) = 0.5 + 0.5 * tanh(y / 2): ONE MUFU op (tanh.approx) instead of ex2 + rcp — the GELU epilogues of
+// the fc1 GEMMs are MUFU-limited (16 lanes/clk/SM on sm_100).  tanh.approx is good to ~2^-11, below bf16's 2^-9.
+__device__ __forceinline__ float fast_sigmoid(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  return fmaf(0.5f, t, 0.5f);
+}
+// QuickGELU = x * sigmoid(1.702 x) (transformers QuickGELUActivation, selected at CLIP_ViP.py:389)
+__device__ __forceinline__ float quick_gelu(float x) { return x * fast_sigmoid(1.702f * x); }
 __device__ __forceinline__ float quick_gelu_grad(float x) {
-  float s = 1.f / (1.f + __expf(-1.702f * x));
-  return s * (1.f + 1.702f * x * (1.f - s));
+  const float s = fast_sigmoid(1.702f * x);
+  return s * fmaf(1.702f * x, 1.f - s, 1.f);
 }
 
 }  // namespace xp

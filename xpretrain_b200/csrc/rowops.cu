@@ -289,6 +289,7 @@ using namespace xp;
 extern "C" int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMap* ymap,
                                 const float* gamma, const float* beta, float* mean, float* rstd, int64_t rows,
                                 int32_t C, float eps, void* stream) {
+  XP_ENTER(x);
   if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_fwd: C must be a multiple of 8 and <= 1024");
   if (rows <= 0) return 0;
   ln_fwd_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -302,6 +303,7 @@ extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const voi
                                 const float* gamma, const float* mean, const float* rstd, const void* dres,
                                 const XpRowMap* drmap, void* dx, const XpRowMap* dxmap, float* dgamma, float* dbeta,
                                 int64_t rows, int32_t C, void* stream) {
+  XP_ENTER(dy);
   if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_bwd: C must be a multiple of 8 and <= 1024");
   if (rows <= 0) return 0;
   long long want = (rows + LNB_WARPS - 1) / LNB_WARPS;
@@ -332,6 +334,7 @@ extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const voi
 }
 
 extern "C" int xp_l2norm_fwd(const float* x, float* y, float* inv_norm, int32_t rows, int32_t C, void* stream) {
+  XP_ENTER(x);
   if (rows <= 0) return 0;
   l2norm_fwd_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, y, inv_norm, rows, C);
   XP_CHECK_LAUNCH("l2norm_fwd_kernel");
@@ -340,6 +343,7 @@ extern "C" int xp_l2norm_fwd(const float* x, float* y, float* inv_norm, int32_t 
 
 extern "C" int xp_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, void* dx_bf16, int32_t rows,
                              int32_t C, float scale, void* stream) {
+  XP_ENTER(dy);
   if (rows <= 0) return 0;
   l2norm_bwd_kernel<<<(rows + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       dy, y, inv_norm, static_cast<__nv_bfloat16*>(dx_bf16), rows, C, scale);
@@ -349,6 +353,7 @@ extern "C" int xp_l2norm_bwd(const float* dy, const float* y, const float* inv_n
 
 extern "C" int xp_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int32_t C, float scale,
                               void* stream) {
+  XP_ENTER(x);
   if (C % 8 || ld % 8) return fail("xp_colsum_bf16: C and ld must be multiples of 8");
   if (rows <= 0) return 0;
   const int gx = (C + 255) / 256;
@@ -362,6 +367,7 @@ extern "C" int xp_colsum_bf16(const void* x, int64_t ld, float* out, int64_t row
 }
 
 extern "C" int xp_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  XP_ENTER(src);
   if (n <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
     return fail("xp_cast_f32_bf16: pointers must be 16-byte aligned");

@@ -171,6 +171,7 @@ using namespace xp;
 
 extern "C" int xp_text_attention_fwd(const void* qkv, const int64_t* mask, void* out, float* probs, int32_t B, int32_t H,
                                      int32_t Lt, int32_t C, void* stream) {
+  XP_ENTER(qkv);
   if (C != H * TA_HD) return fail("xp_text_attention_fwd: head_dim must be 64");
   if (Lt > TA_MAXL || Lt < 1) return fail("xp_text_attention_fwd: 1 <= Lt <= 96");
   const int smem = 3 * Lt * TA_LDS * 4;
@@ -189,6 +190,7 @@ extern "C" int xp_text_attention_fwd(const void* qkv, const int64_t* mask, void*
 
 extern "C" int xp_text_attention_bwd(const void* qkv, const void* dout, const float* probs, void* dqkv, int32_t B,
                                      int32_t H, int32_t Lt, int32_t C, float q_scale, void* stream) {
+  XP_ENTER(qkv);
   if (C != H * TA_HD) return fail("xp_text_attention_bwd: head_dim must be 64");
   if (Lt > TA_MAXL || Lt < 1) return fail("xp_text_attention_bwd: 1 <= Lt <= 96");
   const int smem = (4 * Lt * TA_LDS + 2 * Lt * (Lt + 1)) * 4;

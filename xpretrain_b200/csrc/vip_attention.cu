@@ -527,6 +527,7 @@ extern "C" int64_t xp_vip_attention_workspace_bytes(int32_t B, int32_t H, int32_
 
 extern "C" int xp_vip_attention_fwd(const void* qkv, void* out, float* lse, float* workspace, int32_t B, int32_t H,
                                     int32_t T, int32_t L, int32_t M, int32_t C, void* stream) {
+  XP_ENTER(qkv);
   AttnDims d;
   if (make_dims(d, B, H, T, L, M, C)) return -1;
   const int smem = 3 * ROWS * 128 + 128;
@@ -547,6 +548,7 @@ extern "C" int xp_vip_attention_fwd(const void* qkv, void* out, float* lse, floa
 extern "C" int xp_vip_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                     float* workspace, int32_t B, int32_t H, int32_t T, int32_t L, int32_t M, int32_t C,
                                     float q_scale, void* stream) {
+  XP_ENTER(qkv);
   AttnDims d;
   if (make_dims(d, B, H, T, L, M, C)) return -1;
   const int smem = 4 * ROWS * 128 + 2 * ROWS * 4 + 128;
