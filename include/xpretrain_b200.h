@@ -137,6 +137,12 @@ int xp_eos_offsets(const int64_t* ids, int64_t* offsets, int32_t* index, int32_t
 int64_t xp_vip_attention_workspace_bytes(int32_t B, int32_t H, int32_t T, int32_t M);
 int xp_vip_attention_fwd(const void* qkv, void* out, float* lse, float* workspace, int32_t B, int32_t H, int32_t T,
                          int32_t L, int32_t M, int32_t C, void* stream);
+/* Same contract, tcgen05/TMEM kernel (S and P·V on the 5th-gen tensor cores, softmax thread-per-TMEM-lane). */
+int xp_vip_attention_fwd_tc(const void* qkv, void* out, float* lse, float* workspace, int32_t B, int32_t H, int32_t T,
+                            int32_t L, int32_t M, int32_t C, void* stream);
+/* First half of the above (frame rows + per-frame partials of the global rows, before the combine step). */
+int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float* lse, float* workspace, int32_t B, int32_t H,
+                                    int32_t T, int32_t L, int32_t M, int32_t C, void* stream);
 /* dqkv bf16 [B*S, 3C] = gradient w.r.t. the (un-scaled-q) projection outputs, i.e. the dq part already carries
  * q_scale (CLIP_ViP.py:341), so the QKV dgrad/wgrad GEMMs treat the three thirds uniformly. */
 int xp_vip_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,

@@ -255,6 +255,12 @@ def test_vip_attention_fwd_bwd(dev, B, H, T, L, M):
     ref, ref_lse = _vip_ref(qr, B, H, T, L, M, C)
     assert rel(out, ref.detach()) < 6e-3
     assert float((lse - ref_lse.detach()).abs().max()) < 2e-2
+    # tcgen05 / TMEM forward: same contract
+    out_tc = torch.zeros(B * S, C, dtype=bf16, device=dev)
+    lse_tc = torch.zeros(B, H, S, device=dev)
+    ops.vip_attention_fwd_tc(qkv, out_tc, lse_tc, ws, B, H, T, L, M, C)
+    assert rel(out_tc, ref.detach()) < 6e-3
+    assert float((lse_tc - ref_lse.detach()).abs().max()) < 2e-2
     dout = torch.randn(B * S, C, generator=g).to(dev).to(bf16)
     ref.backward(dout.float())
     dqkv = torch.empty(B * S, 3 * C, dtype=bf16, device=dev)

@@ -63,6 +63,10 @@ SIGNATURES = {
     "xp_vip_attention_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
     "xp_vip_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
+    "xp_vip_attention_fwd_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p]),
+    "xp_vip_attention_fwd_tc_partial": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                c_int, c_void_p]),
     "xp_vip_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_float, c_void_p]),
     "xp_text_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

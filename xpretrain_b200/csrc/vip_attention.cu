@@ -566,3 +566,18 @@ extern "C" int xp_vip_attention_bwd(const void* qkv, const void* out, const void
   XP_CHECK_LAUNCH("vip_attn_bwd_combine_kernel");
   return 0;
 }
+
+// tcgen05 forward (vip_attention_tc.cu) + the shared combine kernel for the global-query rows.
+extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float* lse, float* workspace, int32_t B,
+                                               int32_t H, int32_t T, int32_t L, int32_t M, int32_t C, void* stream);
+extern "C" int xp_vip_attention_fwd_tc(const void* qkv, void* out, float* lse, float* workspace, int32_t B, int32_t H,
+                                       int32_t T, int32_t L, int32_t M, int32_t C, void* stream) {
+  XP_ENTER(qkv);
+  AttnDims d;
+  if (make_dims(d, B, H, T, L, M, C)) return -1;
+  if (xp_vip_attention_fwd_tc_partial(qkv, out, lse, workspace, B, H, T, L, M, C, stream)) return -1;
+  vip_attn_fwd_combine_kernel<<<dim3(H, B), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      workspace, static_cast<__nv_bfloat16*>(out), lse, d);
+  XP_CHECK_LAUNCH("vip_attn_fwd_combine_kernel");
+  return 0;
+}

@@ -203,6 +203,11 @@ def vip_attention_fwd(qkv, out, lse, ws, B, H, T, L, M, C_):
           "xp_vip_attention_fwd")
 
 
+def vip_attention_fwd_tc(qkv, out, lse, ws, B, H, T, L, M, C_):
+    check(lib().xp_vip_attention_fwd_tc(_p(qkv), _p(out), _p(lse), _p(ws), B, H, T, L, M, C_, _stream()),
+          "xp_vip_attention_fwd_tc")
+
+
 def vip_attention_bwd(qkv, out, dout, lse, dqkv, ws, B, H, T, L, M, C_, q_scale):
     check(lib().xp_vip_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(ws), B, H, T, L, M, C_, q_scale,
                                      _stream()), "xp_vip_attention_bwd")
