@@ -1,16 +1,23 @@
 // tcgen05 / TMEM implementation of the video-proxy (ViP) attention of CLIP-ViP (CLIPAttention.forward2,
-// CLIP_ViP.py:332-381) — forward.  One CTA per (batch, head, frame), 128 threads = one thread per TMEM lane
-// (query row), two CTAs per SM (256 TMEM columns each).
+// CLIP_ViP.py:332-381) — forward.  Persistent, warp-specialised, one CTA per SM looping over (batch, head, frame)
+// problems:
 //
-//   stage   q/k/v rows {0..M-1} U {M+t*L ..} of the fused qkv buffer -> shared memory in the UMMA
-//           SWIZZLE_128B K-major layout (cp.async; the same bytes TMA would have produced)
-//   S       = Q'[128 x 64] . K'[208 x 64]^T      tcgen05.mma (SS), fp32 in TMEM columns [0, 208)
-//   softmax thread-per-row on TMEM (tcgen05.ld), P written back as packed bf16 over the dead S columns
-//           (tcgen05.st) — FlashAttention-4 style S/P aliasing, no shared-memory round trip
-//   O       = P[128 x 208] . V'[208 x 64]        tcgen05.mma with the A operand read from TMEM (TS), V' MN-major
-//   epilogue tcgen05.ld O, normalise, 128-byte row stores; the M global-query rows emit per-frame partials
-//           (max, sum, unnormalised O) merged by vip_attn_fwd_combine (vip_attention.cu).
-// q arrives pre-scaled by head_dim**-0.5 from the QKV GEMM epilogue (CLIP_ViP.py:341).
+//   warp 0        producer: cp.async-stages the problem's q/k/v rows into shared memory in the UMMA SWIZZLE_128B
+//                 layout (double buffered, so problem n+1 loads while problem n computes)
+//   warp 1        MMA issuer (one thread): S = Q' K'^T  (tcgen05.mma SS, fp32 in TMEM), then O = P V' with the A
+//                 operand read from TMEM (tcgen05.mma TS) and V' MN-major from shared memory
+//   warps 4-7     softmax warpgroup of query tile 0 (rows 0..127), one thread per TMEM lane
+//   warps 8-11    softmax warpgroup of query tile 1 (rows 128..255)
+//
+// Row layout per problem (frame t of video b, head h):
+//   queries  sQ rows [0, L) = the frame's patch tokens, rows [200, 200+M) = the M global tokens (cls + proxies);
+//            everything else is zero (written once) — row 200 keeps the global rows on a 1024-byte swizzle atom
+//   keys     sK rows [0, L) frame keys (N = 208 MMA), sKg rows [0, M) global keys (N = 16 MMA); same for values
+//   S tile   TMEM columns [0,208) frame keys | [208,224) global keys; P (packed bf16 pairs) overwrites columns
+//            [0,112) of the dead S (FlashAttention-4 style aliasing); O accumulates in columns [128,192)
+// Frame queries see [global ; own frame] keys (CLIP_ViP.py:352-363).  The global queries' softmax over all frames
+// (:366-375) is assembled from per-frame partials (max, sum, unnormalised O) by vip_attn_fwd_combine; their global
+// keys are counted by frame 0 only.  q arrives pre-scaled by head_dim**-0.5 (CLIP_ViP.py:341).
 #include "../../include/xpretrain_b200.h"
 #include "common.h"
 #include "ptx.cuh"
@@ -18,9 +25,12 @@
 namespace xp {
 
 constexpr int TC_HD = 64;
-constexpr int TC_KEYS = 208;      // padded keys per CTA (M + L <= 208), multiple of 16
-constexpr int TC_QROWS = 256;     // two 128-row query tiles
-constexpr int TC_THREADS = 128;
+constexpr int TC_FK = 208;        // frame-key columns (padded), multiple of 16
+constexpr int TC_GK = 16;         // global-key columns (padded)
+constexpr int TC_GROW = 200;      // smem / tile row of the first global query
+constexpr int TC_QROWS = 256;
+constexpr int TC_THREADS = 384;
+constexpr int TC_BUF_BYTES = (TC_QROWS + 2 * TC_FK + 2 * TC_GK) * 128;   // 90112
 constexpr float TC_LOG2E = 1.4426950408889634f;
 
 struct TcDims {
@@ -30,9 +40,6 @@ struct TcDims {
 
 __device__ __forceinline__ uint32_t sw128(uint32_t base, int row, int chunk) {
   return base + row * 128 + ((chunk ^ (row & 7)) << 4);
-}
-__device__ __forceinline__ long long tc_token(const TcDims& d, int b, int t, int i) {
-  return static_cast<long long>(b) * d.S + (i < d.M ? i : d.M + static_cast<long long>(t) * d.L + (i - d.M));
 }
 
 // A operand from TMEM (packed bf16 pairs, lane = row), B from shared memory.
@@ -79,154 +86,217 @@ __device__ __forceinline__ void tc_cp_async16(uint32_t dst, const void* src) {
 }
 
 // part: [B, H, T, M, 66] fp32 = {max, sum, unnormalised out[64]} of the global queries over this frame's keys.
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                        float* __restrict__ part, const TcDims d) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t sQ = (raw + 1023u) & ~1023u;
-  const uint32_t sK = sQ + TC_QROWS * 128;
-  const uint32_t sV = sK + TC_KEYS * 128;
-  uint8_t* tail = smem_raw + (sV + TC_KEYS * 128 - raw);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(tail);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 8);
+  const uint32_t buf0 = (raw + 1023u) & ~1023u;
+  uint8_t* tail = smem_raw + (buf0 + 2 * TC_BUF_BYTES - raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);      // [2] smem buffer filled
+  uint64_t* empty = full + 2;                              // [2] smem buffer consumed
+  uint64_t* s_ready = empty + 2;                           // [2] S of tile j in TMEM
+  uint64_t* p_ready = s_ready + 2;                         // [2] P of tile j in TMEM
+  uint64_t* o_ready = p_ready + 2;                         // [2] O of tile j in TMEM
+  uint64_t* t_free = o_ready + 2;                          // [2] TMEM region of tile j drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_free + 2);
 
-  const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int nq = d.M + d.L;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total = d.B * d.H * d.T;
 
   if (tid == 0) {
-    mbar_init(mbar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_ready[i], 1);
+      mbar_init(&t_free[i], 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  // ---- stage Q' (256 rows), K', V' (208 rows); rows past M+L are zero
-  for (int idx = tid; idx < (TC_QROWS + 2 * TC_KEYS) * 8; idx += TC_THREADS) {
-    int mat, row;
-    const int r8 = idx >> 3, chunk = idx & 7;
-    if (r8 < TC_QROWS) { mat = 0; row = r8; }
-    else if (r8 < TC_QROWS + TC_KEYS) { mat = 1; row = r8 - TC_QROWS; }
-    else { mat = 2; row = r8 - TC_QROWS - TC_KEYS; }
-    const uint32_t dst = sw128(mat == 0 ? sQ : (mat == 1 ? sK : sV), row, chunk);
-    if (row < nq)
-      tc_cp_async16(dst, qkv + tc_token(d, b, t, row) * d.ld_qkv + static_cast<long long>(mat) * d.C + h * TC_HD + chunk * 8);
-    else
-      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0) : "memory");
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  // zero both buffers once: the producer only ever writes rows [0,L) / [200,200+M) / [0,M)
+  for (int i = tid; i < 2 * TC_BUF_BYTES / 16; i += TC_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(buf0 + i * 16), "r"(0) : "memory");
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
 
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, TC_KEYS, 0, 0);   // S = Q' K'^T, both K-major
-  constexpr uint32_t idesc_o = make_idesc_bf16(128, TC_HD, 0, 1);     // O = P V', P from TMEM, V' MN-major
-  const int ntiles = (nq + 127) / 128;
-  uint32_t phase = 0;
-
-  for (int tile = 0; tile < ntiles; ++tile) {
-    if (tid == 0) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem_base, make_smem_desc_sw128(sQ + tile * (128 * 128) + ks * 32, 16, 1024),
-                  make_smem_desc_sw128(sK + ks * 32, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
-      umma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1;
-    tc_fence_after();
-
-    const int row = tile * 128 + tid;
-    const bool grow = row < d.M;                 // a global (cls / proxy) query row
-    const bool mask_gk = grow && (t != 0);       // its global keys are counted by frame 0 only
-    // ---- pass 1: row maximum (keys >= nq are padding)
-    float mx = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < TC_KEYS / 16; ++c) {
-      uint32_t r[16];
-      tmem_ld16(t_lane + c * 16, r);
-      tmem_ld_wait16(r);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int key = c * 16 + i;
-        const bool dead = key >= nq || (mask_gk && key < d.M);
-        mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(r[i]));
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    int n = 0;
+    for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
+      const int s = n & 1;
+      const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
+      mbar_wait(&empty[s], ((n >> 1) & 1) ^ 1);
+      const uint32_t sQ = buf0 + s * TC_BUF_BYTES, sK = sQ + TC_QROWS * 128, sV = sK + TC_FK * 128;
+      const uint32_t sKg = sV + TC_FK * 128, sVg = sKg + TC_GK * 128;
+      const __nv_bfloat16* frame0 = qkv + (static_cast<long long>(b) * d.S + d.M + static_cast<long long>(t) * d.L) * d.ld_qkv + h * TC_HD;
+      const __nv_bfloat16* glob0 = qkv + static_cast<long long>(b) * d.S * d.ld_qkv + h * TC_HD;
+      for (int idx = lane; idx < d.L * 8 * 3; idx += 32) {
+        const int mat = idx / (d.L * 8), rem = idx - mat * (d.L * 8);
+        const int row = rem >> 3, chunk = rem & 7;
+        tc_cp_async16(sw128(mat == 0 ? sQ : (mat == 1 ? sK : sV), row, chunk),
+                      frame0 + static_cast<long long>(row) * d.ld_qkv + mat * d.C + chunk * 8);
       }
-    }
-    const float mb = mx * TC_LOG2E;
-    // ---- pass 2: P = exp(S - max), row sum; packed bf16 P overwrites the S columns already consumed
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < TC_KEYS / 16; ++c) {
-      uint32_t r[16], pk[8];
-      tmem_ld16(t_lane + c * 16, r);
-      tmem_ld_wait16(r);
-      float pv[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int key = c * 16 + i;
-        const bool dead = key >= nq || (mask_gk && key < d.M);
-        pv[i] = dead ? 0.f : tc_exp2(fmaf(__uint_as_float(r[i]), TC_LOG2E, -mb));
-        sum += pv[i];
+      for (int idx = lane; idx < d.M * 8 * 3; idx += 32) {
+        const int mat = idx / (d.M * 8), rem = idx - mat * (d.M * 8);
+        const int row = rem >> 3, chunk = rem & 7;
+        const uint32_t dst = mat == 0 ? sw128(sQ, TC_GROW + row, chunk) : sw128(mat == 1 ? sKg : sVg, row, chunk);
+        tc_cp_async16(dst, glob0 + static_cast<long long>(row) * d.ld_qkv + mat * d.C + chunk * 8);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
-      tmem_st8(t_lane + c * 8, pk);   // columns [8c, 8c+8) <= columns already read ([0, 16c+16))
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
     }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_sf = make_idesc_bf16(128, TC_FK, 0, 0);
+      constexpr uint32_t idesc_sg = make_idesc_bf16(128, TC_GK, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, TC_HD, 0, 1);
+      int n = 0;
+      for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
+        const int s = n & 1;
+        const uint32_t pp = n & 1;
+        const uint32_t sQ = buf0 + s * TC_BUF_BYTES, sK = sQ + TC_QROWS * 128, sV = sK + TC_FK * 128;
+        const uint32_t sKg = sV + TC_FK * 128, sVg = sKg + TC_GK * 128;
+        mbar_wait(&full[s], (n >> 1) & 1);
+        fence_proxy_async_smem();
+        for (int j = 0; j < 2; ++j) {
+          mbar_wait(&t_free[j], pp ^ 1);
+          tc_fence_after();
+          const uint32_t tS = tmem_base + j * 256;
 #pragma unroll
-      for (int ks = 0; ks < TC_KEYS / 16; ++ks)
-        umma_bf16_ts(tmem_base + 128, tmem_base + ks * 8, make_smem_desc_sw128(sV + ks * 2048, TC_KEYS * 128, 1024),
-                     idesc_o, ks > 0 ? 1u : 0u);
-      umma_commit(mbar);
-    }
-    mbar_wait(mbar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue
-    uint32_t o[2][32];
-    tmem_ld32(t_lane + 128, o[0]);
-    tmem_ld32(t_lane + 160, o[1]);
-    tmem_ld_wait(o[0]);
-    tmem_ld_wait(o[1]);
-    if (row < nq) {
-      if (grow) {
-        float* p = part + (((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M + row) * 66;
-        p[0] = mx;
-        p[1] = sum;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) p[2 + i] = __uint_as_float(o[i >> 5][i & 31]);
-      } else {
-        const float inv = 1.f / sum;
-        const long long tok = tc_token(d, b, t, row);
-        __nv_bfloat16* dst = out + tok * d.ld_o + h * TC_HD;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint4 v;
-          const uint32_t* s = &o[q >> 2][(q & 3) * 8];
-          v.x = pack_bf16(__uint_as_float(s[0]) * inv, __uint_as_float(s[1]) * inv);
-          v.y = pack_bf16(__uint_as_float(s[2]) * inv, __uint_as_float(s[3]) * inv);
-          v.z = pack_bf16(__uint_as_float(s[4]) * inv, __uint_as_float(s[5]) * inv);
-          v.w = pack_bf16(__uint_as_float(s[6]) * inv, __uint_as_float(s[7]) * inv);
-          *reinterpret_cast<uint4*>(dst + q * 8) = v;
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t adesc = make_smem_desc_sw128(sQ + j * (128 * 128) + ks * 32, 16, 1024);
+            umma_bf16(tS, adesc, make_smem_desc_sw128(sK + ks * 32, 16, 1024), idesc_sf, ks > 0 ? 1u : 0u);
+            umma_bf16(tS + TC_FK, adesc, make_smem_desc_sw128(sKg + ks * 32, 16, 1024), idesc_sg, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_ready[j]);
         }
-        lse[(static_cast<long long>(b) * d.H + h) * d.S + (tok - static_cast<long long>(b) * d.S)] = mx + logf(sum);
+        for (int j = 0; j < 2; ++j) {
+          mbar_wait(&p_ready[j], pp);
+          tc_fence_after();
+          const uint32_t tP = tmem_base + j * 256, tO = tP + 128;
+#pragma unroll
+          for (int ks = 0; ks < TC_FK / 16; ++ks)
+            umma_bf16_ts(tO, tP + ks * 8, make_smem_desc_sw128(sV + ks * 2048, TC_FK * 128, 1024), idesc_o,
+                         ks > 0 ? 1u : 0u);
+          umma_bf16_ts(tO, tP + TC_FK / 2, make_smem_desc_sw128(sVg, TC_GK * 128, 1024), idesc_o, 1u);
+          umma_commit(&o_ready[j]);
+        }
+        umma_commit(&empty[s]);   // every MMA that reads smem buffer s has been issued
       }
     }
-    tc_fence_before();
-    __syncthreads();   // every thread is done with this tile's TMEM before the next S overwrites it
-    tc_fence_after();
+  } else if (warp >= 4) {
+    // --------------------------------------------------- softmax warpgroups (tile j = 0 / 1)
+    const int j = (warp - 4) >> 2;
+    const int wq = warp & 3;                       // TMEM lane quarter
+    const int trow = wq * 32 + lane;               // row within the tile == TMEM lane
+    const int row = j * 128 + trow;                // row within sQ
+    const bool is_frame = row < d.L;
+    const bool is_glob = row >= TC_GROW && row < TC_GROW + d.M;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + j * 256;
+    int n = 0;
+    for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
+      const uint32_t pp = n & 1;
+      const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
+      const bool mask_gk = is_glob && (t != 0);   // a global query counts the global keys in frame 0 only
+      mbar_wait(&s_ready[j], pp);
+      tc_fence_after();
+      // ---- pass 1: row maximum (software-pipelined TMEM loads)
+      float mx = -INFINITY;
+      uint32_t r[2][16];
+      tmem_ld16(t_lane, r[0]);
+#pragma unroll
+      for (int c = 0; c < (TC_FK + TC_GK) / 16; ++c) {
+        tmem_ld_wait16(r[c & 1]);
+        if (c + 1 < (TC_FK + TC_GK) / 16) tmem_ld16(t_lane + (c + 1) * 16, r[(c + 1) & 1]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = c * 16 + i;
+          const bool dead = col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk);
+          mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(r[c & 1][i]));
+        }
+      }
+      const float mb = mx * TC_LOG2E;
+      // ---- pass 2: P = exp(S - max), row sum; packed bf16 P overwrites S columns already consumed
+      float sum = 0.f;
+      tmem_ld16(t_lane, r[0]);
+#pragma unroll
+      for (int c = 0; c < (TC_FK + TC_GK) / 16; ++c) {
+        tmem_ld_wait16(r[c & 1]);
+        if (c + 1 < (TC_FK + TC_GK) / 16) tmem_ld16(t_lane + (c + 1) * 16, r[(c + 1) & 1]);
+        uint32_t pk[8];
+        float pv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = c * 16 + i;
+          const bool dead = col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk);
+          pv[i] = dead ? 0.f : tc_exp2(fmaf(__uint_as_float(r[c & 1][i]), TC_LOG2E, -mb));
+          sum += pv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+        // chunk c+1 (columns [16c+16, 16c+32)) is already in flight; P goes to columns [8c, 8c+8) < 16c+16
+        tmem_st8(t_lane + c * 8, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[j]);
+      // ---- epilogue
+      mbar_wait(&o_ready[j], pp);
+      tc_fence_after();
+      const long long srow = d.M + static_cast<long long>(t) * d.L + row;      // position in the sequence
+      float* gp = part + (((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M + (row - TC_GROW)) * 66;
+      __nv_bfloat16* dst = out + (static_cast<long long>(b) * d.S + srow) * d.ld_o + h * TC_HD;
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o[32];
+        tmem_ld32(t_lane + 128 + half * 32, o);
+        tmem_ld_wait(o);
+        if (half == 1) {
+          tc_fence_before();
+          mbar_arrive(&t_free[j]);    // registers hold the last of O: the next S may overwrite this TMEM region
+        }
+        if (is_glob) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) gp[2 + half * 32 + i] = __uint_as_float(o[i]);
+        } else if (is_frame) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+            v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+            v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+            v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + half * 32 + q * 8) = v;
+          }
+        }
+      }
+      if (is_glob) {
+        gp[0] = mx;
+        gp[1] = sum;
+      } else if (is_frame) {
+        lse[(static_cast<long long>(b) * d.H + h) * d.S + srow] = mx + logf(sum);
+      }
+    }
   }
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
 }
 
 }  // namespace xp
@@ -237,20 +307,22 @@ extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float
                                                int32_t H, int32_t T, int32_t L, int32_t M, int32_t C, void* stream) {
   XP_ENTER(qkv);
   if (C != H * TC_HD) return fail("vip_attention: head_dim must be 64 (C == 64*H)");
-  if (M + L > TC_KEYS) return fail("vip_attention: M + L must be <= 208");
+  if (L < 1 || L > 196) return fail("vip_attention: 1 <= L <= 196 patch tokens per frame");
   if (M < 1 || M > 8) return fail("vip_attention: 1 <= M <= 8 global tokens");
   TcDims d;
   d.B = B; d.H = H; d.T = T; d.L = L; d.M = M; d.C = C;
   d.S = static_cast<long long>(M) + static_cast<long long>(T) * L;
   d.ld_qkv = 3LL * C;
   d.ld_o = C;
-  const int smem = (TC_QROWS + 2 * TC_KEYS) * 128 + 1024 + 64;
+  const int smem = 2 * TC_BUF_BYTES + 1024 + 128;
   static bool attr = false;
   if (!attr) {
     XP_CHECK_CUDA(cudaFuncSetAttribute(vip_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  vip_attn_fwd_tc_kernel<<<dim3(T, H, B), TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  const long long total = static_cast<long long>(B) * H * T;
+  const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+  vip_attn_fwd_tc_kernel<<<grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, workspace, d);
   XP_CHECK_LAUNCH("vip_attn_fwd_tc_kernel");
   return 0;
