@@ -2,8 +2,8 @@
 // CLIP_ViP.py:332-381) — forward.  Persistent, warp-specialised, one CTA per SM looping over (batch, head, frame)
 // problems:
 //
-//   warp 0        producer: cp.async-stages the problem's q/k/v rows into shared memory in the UMMA SWIZZLE_128B
-//                 layout (double buffered, so problem n+1 loads while problem n computes)
+//   warps 0,2,3   producers: cp.async-stage the problem's q / k / v rows into shared memory in the UMMA
+//                 SWIZZLE_128B layout (double buffered, so problem n+1 loads while problem n computes)
 //   warp 1        MMA issuer (one thread): S = Q' K'^T  (tcgen05.mma SS, fp32 in TMEM), then O = P V' with the A
 //                 operand read from TMEM (tcgen05.mma TS) and V' MN-major from shared memory
 //   warps 4-7     softmax warpgroup of query tile 0 (rows 0..127), one thread per TMEM lane
@@ -106,7 +106,7 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], 3);
       mbar_init(&empty[i], 1);
       mbar_init(&s_ready[i], 1);
       mbar_init(&p_ready[i], 128);
@@ -128,8 +128,10 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ producer
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ------------------------------------------- producers: warp 0 -> Q rows, warp 2 -> K rows, warp 3 -> V rows
+    const int mat = warp == 0 ? 0 : warp - 1;
+    const int chunk = lane & 7, r0 = lane >> 3;     // 4 rows x 8 sixteen-byte chunks per warp instruction
     int n = 0;
     for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
       const int s = n & 1;
@@ -137,20 +139,12 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
       mbar_wait(&empty[s], ((n >> 1) & 1) ^ 1);
       const uint32_t sQ = buf0 + s * TC_BUF_BYTES, sK = sQ + TC_QROWS * 128, sV = sK + TC_FK * 128;
       const uint32_t sKg = sV + TC_FK * 128, sVg = sKg + TC_GK * 128;
-      const __nv_bfloat16* frame0 = qkv + (static_cast<long long>(b) * d.S + d.M + static_cast<long long>(t) * d.L) * d.ld_qkv + h * TC_HD;
-      const __nv_bfloat16* glob0 = qkv + static_cast<long long>(b) * d.S * d.ld_qkv + h * TC_HD;
-      for (int idx = lane; idx < d.L * 8 * 3; idx += 32) {
-        const int mat = idx / (d.L * 8), rem = idx - mat * (d.L * 8);
-        const int row = rem >> 3, chunk = rem & 7;
-        tc_cp_async16(sw128(mat == 0 ? sQ : (mat == 1 ? sK : sV), row, chunk),
-                      frame0 + static_cast<long long>(row) * d.ld_qkv + mat * d.C + chunk * 8);
-      }
-      for (int idx = lane; idx < d.M * 8 * 3; idx += 32) {
-        const int mat = idx / (d.M * 8), rem = idx - mat * (d.M * 8);
-        const int row = rem >> 3, chunk = rem & 7;
-        const uint32_t dst = mat == 0 ? sw128(sQ, TC_GROW + row, chunk) : sw128(mat == 1 ? sKg : sVg, row, chunk);
-        tc_cp_async16(dst, glob0 + static_cast<long long>(row) * d.ld_qkv + mat * d.C + chunk * 8);
-      }
+      const uint32_t dstF = mat == 0 ? sQ : (mat == 1 ? sK : sV);
+      const uint32_t dstG = mat == 0 ? sQ + TC_GROW * 128 : (mat == 1 ? sKg : sVg);   // (TC_GROW & 7) == 0
+      const __nv_bfloat16* gsrc = qkv + static_cast<long long>(b) * d.S * d.ld_qkv + mat * d.C + h * TC_HD + chunk * 8;
+      const __nv_bfloat16* fsrc = gsrc + (d.M + static_cast<long long>(t) * d.L) * d.ld_qkv;
+      for (int row = r0; row < d.L; row += 4) tc_cp_async16(sw128(dstF, row, chunk), fsrc + static_cast<long long>(row) * d.ld_qkv);
+      for (int row = r0; row < d.M; row += 4) tc_cp_async16(sw128(dstG, row, chunk), gsrc + static_cast<long long>(row) * d.ld_qkv);
       asm volatile("cp.async.wait_all;" ::: "memory");
       fence_proxy_async_smem();
       __syncwarp();
@@ -205,6 +199,8 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     const bool is_frame = row < d.L;
     const bool is_glob = row >= TC_GROW && row < TC_GROW + d.M;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + j * 256;
+    // a warp whose 32 rows hold neither frame nor global queries only takes part in the barrier protocol
+    const bool warp_active = (j * 128 + wq * 32 < d.L) || (j * 128 + wq * 32 + 31 >= TC_GROW && j * 128 + wq * 32 < TC_GROW + d.M);
     int n = 0;
     for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
       const uint32_t pp = n & 1;
@@ -212,42 +208,59 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
       const bool mask_gk = is_glob && (t != 0);   // a global query counts the global keys in frame 0 only
       mbar_wait(&s_ready[j], pp);
       tc_fence_after();
-      // ---- pass 1: row maximum (software-pipelined TMEM loads)
+      // ---- pass 1: row maximum (software-pipelined TMEM loads; chunks with only live keys skip the masks)
       float mx = -INFINITY;
       uint32_t r[2][16];
-      tmem_ld16(t_lane, r[0]);
+      if (warp_active) {
+        tmem_ld16(t_lane, r[0]);
 #pragma unroll
-      for (int c = 0; c < (TC_FK + TC_GK) / 16; ++c) {
-        tmem_ld_wait16(r[c & 1]);
-        if (c + 1 < (TC_FK + TC_GK) / 16) tmem_ld16(t_lane + (c + 1) * 16, r[(c + 1) & 1]);
+        for (int c = 0; c < (TC_FK + TC_GK) / 16; ++c) {
+          tmem_ld_wait16(r[c & 1]);
+          if (c + 1 < (TC_FK + TC_GK) / 16) tmem_ld16(t_lane + (c + 1) * 16, r[(c + 1) & 1]);
+          if (c * 16 + 16 <= d.L) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = c * 16 + i;
-          const bool dead = col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk);
-          mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(r[c & 1][i]));
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[c & 1][i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c * 16 + i;
+              const bool dead = col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk);
+              mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(r[c & 1][i]));
+            }
+          }
         }
       }
       const float mb = mx * TC_LOG2E;
       // ---- pass 2: P = exp(S - max), row sum; packed bf16 P overwrites S columns already consumed
       float sum = 0.f;
-      tmem_ld16(t_lane, r[0]);
+      if (warp_active) {
+        tmem_ld16(t_lane, r[0]);
 #pragma unroll
-      for (int c = 0; c < (TC_FK + TC_GK) / 16; ++c) {
-        tmem_ld_wait16(r[c & 1]);
-        if (c + 1 < (TC_FK + TC_GK) / 16) tmem_ld16(t_lane + (c + 1) * 16, r[(c + 1) & 1]);
-        uint32_t pk[8];
-        float pv[16];
+        for (int c = 0; c < (TC_FK + TC_GK) / 16; ++c) {
+          tmem_ld_wait16(r[c & 1]);
+          if (c + 1 < (TC_FK + TC_GK) / 16) tmem_ld16(t_lane + (c + 1) * 16, r[(c + 1) & 1]);
+          uint32_t pk[8];
+          float pv[16];
+          if (c * 16 + 16 <= d.L) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = c * 16 + i;
-          const bool dead = col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk);
-          pv[i] = dead ? 0.f : tc_exp2(fmaf(__uint_as_float(r[c & 1][i]), TC_LOG2E, -mb));
-          sum += pv[i];
+            for (int i = 0; i < 16; ++i) {
+              pv[i] = tc_exp2(fmaf(__uint_as_float(r[c & 1][i]), TC_LOG2E, -mb));
+              sum += pv[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c * 16 + i;
+              const bool dead = col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk);
+              pv[i] = dead ? 0.f : tc_exp2(fmaf(__uint_as_float(r[c & 1][i]), TC_LOG2E, -mb));
+              sum += pv[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+          // chunk c+1 (columns [16c+16, 16c+32)) is already in flight; P goes to columns [8c, 8c+8) < 16c+16
+          tmem_st8(t_lane + c * 8, pk);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
-        // chunk c+1 (columns [16c+16, 16c+32)) is already in flight; P goes to columns [8c, 8c+8) < 16c+16
-        tmem_st8(t_lane + c * 8, pk);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -262,8 +275,10 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t o[32];
-        tmem_ld32(t_lane + 128 + half * 32, o);
-        tmem_ld_wait(o);
+        if (warp_active) {
+          tmem_ld32(t_lane + 128 + half * 32, o);
+          tmem_ld_wait(o);
+        }
         if (half == 1) {
           tc_fence_before();
           mbar_arrive(&t_free[j]);    // registers hold the last of O: the next S may overwrite this TMEM region
