@@ -387,7 +387,7 @@ def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
 
     def attn_fwd(qkv, out):
         lse = torch.empty(B, H, S, dtype=f32, device=dev)
-        ops.vip_attention_fwd(qkv, out, lse, ws, B, H, T, L, M, C_)
+        ops.vip_attention_fwd_tc(qkv, out, lse, ws, B, H, T, L, M, C_)
         return lse
 
     layer_saved = []
