@@ -119,6 +119,8 @@ def run_ours(args):
         model.clipmodel.vision_model.embeddings.temporal_embedding.normal_(0, 0.02)
     model = model.to(dev)
     params = [p for p in model.parameters()]
+    if world > 1:   # DP gradient averaging overlapped with backward (logit_scale's gradient is identical on all ranks)
+        model.clipmodel.grad_ready_hook = xdist.OverlappedGradAverager()
 
     # synthetic inputs: pinned host copies for the e2e leg, device copies for the resident leg
     g = torch.Generator().manual_seed(1234 + rank)
@@ -137,7 +139,6 @@ def run_ours(args):
         out = model(video=video, text_input_ids=ids, text_input_mask=mask)
         loss = gather_nce_loss(out["vis_features"], out["text_features"], model.clipmodel.logit_scale)
         loss.backward()
-        xdist.average_gradients(params)
         return loss
 
     def barrier():

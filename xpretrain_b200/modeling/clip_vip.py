@@ -326,14 +326,37 @@ def _layer_bwd(dx, saved, layer, pk: _WeightPack, i: int, grads: Dict[str, torch
     return dxin
 
 
-def _alloc_layer_grads(layer, prefix: str, grads: Dict[str, torch.Tensor], dev):
+def _alloc_flat(shapes: Dict[str, tuple], grads: Dict[str, torch.Tensor], dev) -> torch.Tensor:
+    """One zeroed fp32 buffer holding all gradients of a group as 16-byte aligned views: the data-parallel
+    all-reduce of the group is then a single collective on `flat` (no packing copies)."""
+    offs, total = {}, 0
+    for n, shp in shapes.items():
+        offs[n] = total
+        total += (int(torch.Size(shp).numel()) + 3) // 4 * 4
+    flat = torch.zeros(total, dtype=f32, device=dev)
+    for n, shp in shapes.items():
+        grads[n] = flat[offs[n]:offs[n] + torch.Size(shp).numel()].view(shp)
+    return flat
+
+
+def _alloc_layer_grads(layer, prefix: str, grads: Dict[str, torch.Tensor], dev) -> torch.Tensor:
     C_ = layer.self_attn.q_proj.weight.shape[0]
-    grads[prefix + "self_attn.qkv.weight"] = torch.zeros(3 * C_, C_, dtype=f32, device=dev)
-    grads[prefix + "self_attn.qkv.bias"] = torch.zeros(3 * C_, dtype=f32, device=dev)
+    shapes = {prefix + "self_attn.qkv.weight": (3 * C_, C_), prefix + "self_attn.qkv.bias": (3 * C_,)}
     for n, p in layer.named_parameters():
         if ".q_proj." in n or ".k_proj." in n or ".v_proj." in n:
             continue
-        grads[prefix + n] = torch.zeros(p.shape, dtype=f32, device=dev)
+        shapes[prefix + n] = tuple(p.shape)
+    return _alloc_flat(shapes, grads, dev)
+
+
+def _grads_ready(model, grads: Dict[str, torch.Tensor], key: str) -> None:
+    """A gradient group (one encoder layer, or a tower's remaining parameters) is final: hand its flat buffer to
+    `model.grad_ready_hook` (e.g. utils.distributed.OverlappedGradAverager, which starts an async NCCL all-reduce
+    that overlaps with the rest of the backward pass — the hvd.DistributedOptimizer hooks of run_pretrain.py:226-228)."""
+    hook = getattr(model, "grad_ready_hook", None)
+    flat = grads.get("__flat__" + key)
+    if hook is not None and flat is not None:
+        hook(flat)
 
 
 def _finish_layer_grads(prefix: str, grads: Dict[str, torch.Tensor], C_: int):
@@ -435,6 +458,7 @@ def _vision_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str,
         prefix = f"vision_model.encoder.layers.{i}."
         dx = _layer_bwd(dx, sv.layers[i], vm.encoder.layers[i], pk, i, grads, prefix, attn_bwd, rows)
         sv.layers[i] = None
+        _grads_ready(model, grads, prefix)
     # pre_layrnorm backward, written as two compact halves: patch rows [B, T*L, C] and global rows [B, M, C]
     d_patch = torch.empty(B * T * L, C_, dtype=bf16, device=dev)
     d_glob = torch.empty(B * M, C_, dtype=bf16, device=dev)
@@ -521,6 +545,7 @@ def _text_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str, t
         prefix = f"text_model.encoder.layers.{i}."
         dx = _layer_bwd(dx, sv.layers[i], tm.encoder.layers[i], pk, i, grads, prefix, attn_bwd, rows)
         sv.layers[i] = None
+        _grads_ready(model, grads, prefix)
     ops.text_embed_bwd(sv.ids, dx, grads["text_model.embeddings.token_embedding.weight"],
                        grads["text_model.embeddings.position_embedding.weight"], Lt, C_, cfg.vocab_size)
 
@@ -571,11 +596,11 @@ class _ClipVipFunction(torch.autograd.Function):
                 continue
             tw = getattr(model, tower)
             for i, layer in enumerate(tw.encoder.layers):
-                _alloc_layer_grads(layer, f"{tower}.encoder.layers.{i}.", grads, dev)
-            for n in names:
-                if n.startswith(tower + ".") and ".encoder.layers." not in n:
-                    grads[n] = torch.zeros(named[n].shape, dtype=f32, device=dev)
-            grads[proj_name] = torch.zeros(named[proj_name].shape, dtype=f32, device=dev)
+                pre = f"{tower}.encoder.layers.{i}."
+                grads["__flat__" + pre] = _alloc_layer_grads(layer, pre, grads, dev)
+            rest = {n: tuple(named[n].shape) for n in names if n.startswith(tower + ".") and ".encoder.layers." not in n}
+            rest[proj_name] = tuple(named[proj_name].shape)
+            grads["__flat__" + tower] = _alloc_flat(rest, grads, dev)
             dproj = torch.empty(dfeat.shape, dtype=bf16, device=dev)
             dfeat = dfeat.contiguous().to(f32)
             if ctx.normalize:
@@ -583,8 +608,12 @@ class _ClipVipFunction(torch.autograd.Function):
             else:
                 dproj.copy_(dfeat)
             bwd(model, dproj, sv, grads)
+            _grads_ready(model, grads, tower)
             for i in range(len(tw.encoder.layers)):
                 _finish_layer_grads(f"{tower}.encoder.layers.{i}.", grads, C_)
+        hook = getattr(model, "grad_ready_hook", None)
+        if hook is not None and hasattr(hook, "finish"):
+            hook.finish()      # stream-ordered wait: autograd's accumulation below sees the averaged values
         ctx.vis = ctx.txt = None
         return (None, None, None, None, None) + tuple(grads.get(n) for n in names)
 

@@ -85,3 +85,25 @@ def average_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_b
         if size >= bucket_bytes:
             flush()
     flush()
+
+
+class OverlappedGradAverager:
+    """`model.clipmodel.grad_ready_hook = OverlappedGradAverager()` averages parameter gradients across ranks WHILE
+    backward is still running: every finished gradient group arrives as one flat fp32 buffer and is all-reduced
+    (ReduceOp.AVG) asynchronously on NCCL's stream; `finish()` (called at the end of the model's backward) makes
+    the compute stream wait for the outstanding collectives.  Equivalent to hvd.DistributedOptimizer's backward
+    hooks + synchronize() (run_pretrain.py:226-228,379)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.pending = []
+
+    def __call__(self, flat: torch.Tensor) -> None:
+        if world_size(self.group) == 1:
+            return
+        self.pending.append(dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+
+    def finish(self) -> None:
+        for work in self.pending:
+            work.wait()
+        self.pending = []
