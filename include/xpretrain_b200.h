@@ -149,6 +149,15 @@ int xp_vip_attention_bwd(const void* qkv, const void* out, const void* dout, con
                          float* workspace, int32_t B, int32_t H, int32_t T, int32_t L, int32_t M, int32_t C,
                          float q_scale, void* stream);
 
+/* tcgen05/TMEM backward: S, dP, dV, dK, dQ on the 5th-gen tensor cores.  delta f32 [B, H, S] is scratch that
+ * receives rowsum(dout * out). */
+int xp_vip_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                            float* workspace, float* delta, int32_t B, int32_t H, int32_t T, int32_t L, int32_t M,
+                            int32_t C, float q_scale, void* stream);
+int xp_vip_attention_bwd_tc_partial(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                    float* workspace, float* delta, int32_t B, int32_t H, int32_t T, int32_t L,
+                                    int32_t M, int32_t C, float q_scale, void* stream);
+
 /* ------------------------------------------------------- text-tower attention --
  * CLIPAttention.forward (CLIP_ViP.py:266-330) between the QKV projection and out_proj, with the causal mask
  * (CLIP_ViP.py:788-797) and the padding mask built from attention_mask int64 [B, Lt] (CLIP_ViP.py:50-61).

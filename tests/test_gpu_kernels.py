@@ -265,9 +265,13 @@ def test_vip_attention_fwd_bwd(dev, B, H, T, L, M):
     ref.backward(dout.float())
     dqkv = torch.empty(B * S, 3 * C, dtype=bf16, device=dev)
     ops.vip_attention_bwd(qkv, out, dout, lse, dqkv, ws, B, H, T, L, M, C, 1.0)
-    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
-        assert rel(dqkv[:, sl], qr.grad[:, sl]) < 2e-2, name
-        assert rel(dqkv.view(B, S, 3 * C)[:, :M, sl], qr.grad.view(B, S, 3 * C)[:, :M, sl]) < 2e-2, name + " (global rows)"
+    dqkv_tc = torch.zeros(B * S, 3 * C, dtype=bf16, device=dev)
+    delta = torch.empty(B, H, S, device=dev)
+    ops.vip_attention_bwd_tc(qkv, out_tc, dout, lse_tc, dqkv_tc, ws, delta, B, H, T, L, M, C, 1.0)
+    for impl, got in (("mma.sync", dqkv), ("tcgen05", dqkv_tc)):
+        for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+            assert rel(got[:, sl], qr.grad[:, sl]) < 2e-2, (impl, name)
+            assert rel(got.view(B, S, 3 * C)[:, :M, sl], qr.grad.view(B, S, 3 * C)[:, :M, sl]) < 2e-2, (impl, name, "global rows")
 
 
 @pytest.mark.parametrize("Lt", [32, 77, 5])

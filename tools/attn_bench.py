@@ -13,6 +13,7 @@ out = torch.empty(B * S, C, dtype=torch.bfloat16, device=dev)
 dout = torch.randn(B * S, C, device=dev).to(torch.bfloat16)
 dqkv = torch.empty_like(qkv)
 lse = torch.empty(B, H, S, device=dev)
+delta = torch.empty(B, H, S, device=dev)
 ws = ops.vip_attention_workspace(B, H, T, M, dev)
 
 
@@ -34,7 +35,7 @@ cases = [("fwd mma.sync", lambda: ops.vip_attention_fwd(qkv, out, lse, ws, B, H,
 if hasattr(ops, "vip_attention_fwd_tc"):
     cases.insert(1, ("fwd tcgen05", lambda: ops.vip_attention_fwd_tc(qkv, out, lse, ws, B, H, T, L, M, C), fl_f))
 if hasattr(ops, "vip_attention_bwd_tc"):
-    cases.append(("bwd tcgen05", lambda: ops.vip_attention_bwd_tc(qkv, out, dout, lse, dqkv, ws, B, H, T, L, M, C, 0.125), 2.5 * fl_f))
+    cases.append(("bwd tcgen05", lambda: ops.vip_attention_bwd_tc(qkv, out, dout, lse, dqkv, ws, delta, B, H, T, L, M, C, 0.125), 2.5 * fl_f))
 for name, fn, fl in cases:
     ms = timeit(fn)
     print(f"{name:14s} B={B}: {ms:8.3f} ms   {fl / ms / 1e9:8.1f} TFLOP/s (algorithmic)   -> {ms * 64 / B:7.3f} ms per layer at B=64")

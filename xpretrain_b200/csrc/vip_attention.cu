@@ -581,3 +581,21 @@ extern "C" int xp_vip_attention_fwd_tc(const void* qkv, void* out, float* lse, f
   XP_CHECK_LAUNCH("vip_attn_fwd_combine_kernel");
   return 0;
 }
+
+// tcgen05 backward (vip_attention_tc.cu) + the shared combine kernel for the M global rows.
+extern "C" int xp_vip_attention_bwd_tc_partial(const void* qkv, const void* out, const void* dout, const float* lse,
+                                               void* dqkv, float* workspace, float* delta, int32_t B, int32_t H,
+                                               int32_t T, int32_t L, int32_t M, int32_t C, float q_scale, void* stream);
+extern "C" int xp_vip_attention_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                       float* workspace, float* delta, int32_t B, int32_t H, int32_t T, int32_t L,
+                                       int32_t M, int32_t C, float q_scale, void* stream) {
+  XP_ENTER(qkv);
+  AttnDims d;
+  if (make_dims(d, B, H, T, L, M, C)) return -1;
+  if (xp_vip_attention_bwd_tc_partial(qkv, out, dout, lse, dqkv, workspace, delta, B, H, T, L, M, C, q_scale, stream))
+    return -1;
+  vip_attn_bwd_combine_kernel<<<dim3(H, B), 192, 0, static_cast<cudaStream_t>(stream)>>>(
+      workspace, static_cast<__nv_bfloat16*>(dqkv), d, q_scale);
+  XP_CHECK_LAUNCH("vip_attn_bwd_combine_kernel");
+  return 0;
+}

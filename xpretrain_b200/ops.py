@@ -213,6 +213,11 @@ def vip_attention_bwd(qkv, out, dout, lse, dqkv, ws, B, H, T, L, M, C_, q_scale)
                                      _stream()), "xp_vip_attention_bwd")
 
 
+def vip_attention_bwd_tc(qkv, out, dout, lse, dqkv, ws, delta, B, H, T, L, M, C_, q_scale):
+    check(lib().xp_vip_attention_bwd_tc(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(ws), _p(delta), B, H, T, L, M,
+                                        C_, q_scale, _stream()), "xp_vip_attention_bwd_tc")
+
+
 def text_attention_fwd(qkv, mask, out, probs, B, H, Lt, C_):
     check(lib().xp_text_attention_fwd(_p(qkv), _p(mask), _p(out), _p(probs), B, H, Lt, C_, _stream()),
           "xp_text_attention_fwd")
