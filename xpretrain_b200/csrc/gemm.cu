@@ -222,7 +222,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = ew >> 2;
     const int etid = threadIdx.x - 128;  // 0..255
     constexpr int CHUNKS = BN / 64;      // 32-column chunks per warp per tile
+    // kernel parameters used per element live in registers (the asm "memory" clobbers would otherwise force
+    // ptxas to re-read them from the constant bank inside the loops)
     const bool wide = p.wide != 0;       // every bf16 row segment is 32-byte aligned -> 256-bit accesses
+    const int act = p.act, N = p.N, scale_cols = p.scale_cols;
+    const float alpha = p.alpha, col_scale = p.col_scale;
+    __nv_bfloat16* const aux_p = p.aux;
+    const bool need_aux_in = (act == XP_ACT_DQUICK_GELU || act == XP_ACT_DGELU_ERF);
+    // the one extra bf16 INPUT the epilogue streams: the saved pre-activation (dGELU) or the residual
+    const __nv_bfloat16* const xin_p = need_aux_in ? p.aux : p.residual;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -237,21 +245,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       float* sbias = bias_smem + acc * BN;
       for (int i = etid; i < BN; i += EPI_THREADS) {
         const int n = n_blk * BN + i;
-        sbias[i] = (p.bias != nullptr && n < p.N && split == 0) ? p.bias[n] : 0.f;
+        sbias[i] = (p.bias != nullptr && n < N && split == 0) ? p.bias[n] : 0.f;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-      long long c_off = 0, r_off = 0;
+      long long c_off = 0, x_off = 0;
       if (row_ok) {
         c_off = p.c_group > 0 ? (row / p.c_group) * p.c_group_stride + (row % p.c_group) * p.ldc
                               : static_cast<long long>(row) * p.ldc;
-        r_off = p.r_group > 0 ? (row / p.r_group) * p.r_group_stride + (row % p.r_group) * p.ldr
-                              : static_cast<long long>(row) * p.ldr;
+        x_off = need_aux_in ? static_cast<long long>(row) * p.ld_aux
+                            : (p.r_group > 0 ? (row / p.r_group) * p.r_group_stride + (row % p.r_group) * p.ldr
+                                             : static_cast<long long>(row) * p.ldr);
       }
       const long long a_off = static_cast<long long>(row) * p.ld_aux;
+      const int ncol0 = n_blk * BN + half * (BN / 2);   // first global column of this warp's half
+      // software pipeline of the extra input: chunk c+1's global reads are in flight while chunk c is processed,
+      // and chunk 0's are issued BEFORE waiting for the accumulator (their latency hides behind the MMAs)
+      uint32_t xin[2][2][8];
+      auto issue_xin = [&](int c, uint32_t (&dst)[2][8]) {
+        if (xin_p == nullptr || !row_ok) return;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int n = ncol0 + c * 32 + g * 16;
+          if (n < N) ld_bf16x16(xin_p + x_off + n, wide && (n + 16 <= N), n + 8 < N, dst[g]);
+        }
+      };
+      issue_xin(0, xin[0]);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
       uint32_t rbuf[2][32];
       tmem_ld32(t_row, rbuf[0]);
@@ -259,71 +281,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int c = 0; c < CHUNKS; ++c) {
         uint32_t(&r)[32] = rbuf[c & 1];
         tmem_ld_wait(r);
-        if (c + 1 < CHUNKS) tmem_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);  // overlaps the math below
+        if (c + 1 < CHUNKS) {
+          tmem_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);  // overlaps the math below
+          issue_xin(c + 1, xin[(c + 1) & 1]);
+        }
         const int nl = half * (BN / 2) + c * 32;  // column within the tile
         const int n0 = n_blk * BN + nl;
-        if (row_ok && n0 < p.N) {
+        if (row_ok && n0 < N) {
           // two groups of 16 columns: 32-byte global accesses (one full sector per lane) when `wide`
-          const bool need_aux_in = (p.act == XP_ACT_DQUICK_GELU || p.act == XP_ACT_DGELU_ERF);
-          uint32_t rres[2][8], raux[2][8];
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {  // issue this chunk's global reads first so their latency overlaps
-            const int n = n0 + g * 16;
-            if (n < p.N) {
-              const bool full = wide && (n + 16 <= p.N);
-              if (p.residual != nullptr) ld_bf16x16(p.residual + r_off + n, full, n + 8 < p.N, rres[g]);
-              if (need_aux_in) ld_bf16x16(p.aux + a_off + n, full, n + 8 < p.N, raux[g]);
-            }
-          }
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int n = n0 + g * 16;
-            if (n < p.N) {
-              const bool second = n + 8 < p.N;          // N % 8 == 0: a group holds 8 or 16 valid columns
-              const bool full = wide && (n + 16 <= p.N);
+            if (n < N) {
+              const bool second = n + 8 < N;          // N % 8 == 0: a group holds 8 or 16 valid columns
+              const bool full = wide && (n + 16 <= N);
+              const uint32_t(&xg)[8] = xin[c & 1][g];
               float v[16];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 b = *reinterpret_cast<const float4*>(sbias + nl + g * 16 + q * 4);
-                v[q * 4 + 0] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 0]), p.alpha, b.x);
-                v[q * 4 + 1] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 1]), p.alpha, b.y);
-                v[q * 4 + 2] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 2]), p.alpha, b.z);
-                v[q * 4 + 3] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 3]), p.alpha, b.w);
+                v[q * 4 + 0] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 0]), alpha, b.x);
+                v[q * 4 + 1] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 1]), alpha, b.y);
+                v[q * 4 + 2] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 2]), alpha, b.z);
+                v[q * 4 + 3] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 3]), alpha, b.w);
               }
-              if (n < p.scale_cols) {
+              if (n < scale_cols) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= p.col_scale;
-                if (n + 8 < p.scale_cols) {
+                for (int i = 0; i < 8; ++i) v[i] *= col_scale;
+                if (n + 8 < scale_cols) {
 #pragma unroll
-                  for (int i = 8; i < 16; ++i) v[i] *= p.col_scale;
+                  for (int i = 8; i < 16; ++i) v[i] *= col_scale;
                 }
               }
-              if (p.act == XP_ACT_QUICK_GELU) {
-                if (p.aux != nullptr) st_bf16x16(p.aux + a_off + n, full, second, v);
+              if (act == XP_ACT_QUICK_GELU) {
+                if (aux_p != nullptr) st_bf16x16(aux_p + a_off + n, full, second, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = quick_gelu(v[i]);
-              } else if (p.act == XP_ACT_DQUICK_GELU) {
+              } else if (act == XP_ACT_DQUICK_GELU) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  v[2 * i] *= quick_gelu_grad(bf16_lo(raux[g][i]));
-                  v[2 * i + 1] *= quick_gelu_grad(bf16_hi(raux[g][i]));
+                  v[2 * i] *= quick_gelu_grad(bf16_lo(xg[i]));
+                  v[2 * i + 1] *= quick_gelu_grad(bf16_hi(xg[i]));
                 }
-              } else if (p.act == XP_ACT_GELU_ERF) {
-                if (p.aux != nullptr) st_bf16x16(p.aux + a_off + n, full, second, v);
+              } else if (act == XP_ACT_GELU_ERF) {
+                if (aux_p != nullptr) st_bf16x16(aux_p + a_off + n, full, second, v);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = act_gelu_erf(v[i]);
-              } else if (p.act == XP_ACT_DGELU_ERF) {
+              } else if (act == XP_ACT_DGELU_ERF) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  v[2 * i] *= act_gelu_erf_grad(bf16_lo(raux[g][i]));
-                  v[2 * i + 1] *= act_gelu_erf_grad(bf16_hi(raux[g][i]));
+                  v[2 * i] *= act_gelu_erf_grad(bf16_lo(xg[i]));
+                  v[2 * i + 1] *= act_gelu_erf_grad(bf16_hi(xg[i]));
                 }
-              }
-              if (p.residual != nullptr) {
+              } else if (xin_p != nullptr) {   // residual add (never combined with a dGELU epilogue)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  v[2 * i] += bf16_lo(rres[g][i]);
-                  v[2 * i + 1] += bf16_hi(rres[g][i]);
+                  v[2 * i] += bf16_lo(xg[i]);
+                  v[2 * i + 1] += bf16_hi(xg[i]);
                 }
               }
               if (OUT == XP_OUT_BF16) {
@@ -419,6 +433,8 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
   if (splits > 1 && g->out != XP_OUT_F32_ATOMIC) return fail("xp_gemm: split-K requires XP_OUT_F32_ATOMIC");
   if ((g->act == XP_ACT_DQUICK_GELU || g->act == XP_ACT_DGELU_ERF) && !g->aux)
     return fail("xp_gemm: dGELU epilogue needs aux (the forward pre-activation)");
+  if ((g->act == XP_ACT_DQUICK_GELU || g->act == XP_ACT_DGELU_ERF) && g->residual)
+    return fail("xp_gemm: a dGELU epilogue cannot be combined with a residual add");
   const int elem_c = g->out == XP_OUT_BF16 ? 2 : 4;
   if ((reinterpret_cast<uintptr_t>(g->c) & 15) || (g->ldc * elem_c) % 16)
     return fail("xp_gemm: C must be 16-byte aligned with a 16-byte multiple row pitch");
