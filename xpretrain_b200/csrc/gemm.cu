@@ -74,7 +74,7 @@ __device__ __forceinline__ void ld_bf16x16(const __nv_bfloat16* ptr, bool wide, 
 __device__ __forceinline__ void st_bf16x16(__nv_bfloat16* ptr, bool wide, bool second, const float (&v)[16]) {
   uint32_t w[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+  for (int i = 0; i < 8; ++i) w[i] = pack_bf16_fma(v[2 * i], v[2 * i + 1]);
   if (wide) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                  "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
