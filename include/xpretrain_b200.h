@@ -67,6 +67,8 @@ typedef struct XpGemm {
   int64_t c_group, c_group_stride, r_group, r_group_stride;
   int32_t block_n;    /* 0 = auto, else 128 or 256 */
   int32_t max_ctas;   /* 0 = one persistent CTA per SM */
+  int32_t cta_pair;   /* 0 = auto (2-CTA cta_group::2 pairs on 256x256 tiles when M, N >= 256), 1 = never, 2 = force */
+  int32_t reserved;
 } XpGemm;
 
 int xp_gemm(const XpGemm* g, void* stream);

@@ -66,5 +66,5 @@ def test_wgrad_plan_fills_waves():
     from xpretrain_b200.ops import wgrad_plan
     for n_out, n_in in [(3072, 768), (768, 3072), (2304, 768), (768, 768)]:
         bn, s = wgrad_plan(n_out, n_in, 150784)
-        tiles = ((n_out + 127) // 128) * ((n_in + bn - 1) // bn) * s
-        assert tiles / (-(-tiles // 148) * 148) > 0.9
+        tiles = ((n_out + 255) // 256) * ((n_in + 255) // 256) * s        # CTA pairs: 256 x 256 tiles on 74 clusters
+        assert tiles / (-(-tiles // 74) * 74) > 0.9

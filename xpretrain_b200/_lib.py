@@ -23,7 +23,7 @@ class XpGemm(C.Structure):
         ("a_layout", c_int), ("b_layout", c_int), ("act", c_int), ("out", c_int),
         ("splits", c_int), ("scale_cols", c_int), ("alpha", c_float), ("col_scale", c_float),
         ("c_group", c_i64), ("c_group_stride", c_i64), ("r_group", c_i64), ("r_group_stride", c_i64),
-        ("block_n", c_int), ("max_ctas", c_int),
+        ("block_n", c_int), ("max_ctas", c_int), ("cta_pair", c_int), ("reserved", c_int),
     ]
 
 

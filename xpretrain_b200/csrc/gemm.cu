@@ -74,7 +74,7 @@ __device__ __forceinline__ void ld_bf16x16(const __nv_bfloat16* ptr, bool wide, 
 __device__ __forceinline__ void st_bf16x16(__nv_bfloat16* ptr, bool wide, bool second, const float (&v)[16]) {
   uint32_t w[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) w[i] = pack_bf16_fma(v[2 * i], v[2 * i + 1]);
+  for (int i = 0; i < 8; ++i) w[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
   if (wide) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                  "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
@@ -249,118 +249,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-      long long c_off = 0, x_off = 0;
-      if (row_ok) {
-        c_off = p.c_group > 0 ? (row / p.c_group) * p.c_group_stride + (row % p.c_group) * p.ldc
-                              : static_cast<long long>(row) * p.ldc;
-        x_off = need_aux_in ? static_cast<long long>(row) * p.ld_aux
-                            : (p.r_group > 0 ? (row / p.r_group) * p.r_group_stride + (row % p.r_group) * p.ldr
-                                             : static_cast<long long>(row) * p.ldr);
-      }
-      const long long a_off = static_cast<long long>(row) * p.ld_aux;
-      const int ncol0 = n_blk * BN + half * (BN / 2);   // first global column of this warp's half
-      // software pipeline of the extra input: chunk c+1's global reads are in flight while chunk c is processed,
-      // and chunk 0's are issued BEFORE waiting for the accumulator (their latency hides behind the MMAs)
-      uint32_t xin[2][2][8];
-      auto issue_xin = [&](int c, uint32_t (&dst)[2][8]) {
-        if (xin_p == nullptr || !row_ok) return;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int n = ncol0 + c * 32 + g * 16;
-          if (n < N) ld_bf16x16(xin_p + x_off + n, wide && (n + 16 <= N), n + 8 < N, dst[g]);
-        }
-      };
-      issue_xin(0, xin[0]);
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
-      uint32_t rbuf[2][32];
-      tmem_ld32(t_row, rbuf[0]);
-#pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) {
-        uint32_t(&r)[32] = rbuf[c & 1];
-        tmem_ld_wait(r);
-        if (c + 1 < CHUNKS) {
-          tmem_ld32(t_row + (c + 1) * 32, rbuf[(c + 1) & 1]);  // overlaps the math below
-          issue_xin(c + 1, xin[(c + 1) & 1]);
-        }
-        const int nl = half * (BN / 2) + c * 32;  // column within the tile
-        const int n0 = n_blk * BN + nl;
-        if (row_ok && n0 < N) {
-          // two groups of 16 columns: 32-byte global accesses (one full sector per lane) when `wide`
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int n = n0 + g * 16;
-            if (n < N) {
-              const bool second = n + 8 < N;          // N % 8 == 0: a group holds 8 or 16 valid columns
-              const bool full = wide && (n + 16 <= N);
-              const uint32_t(&xg)[8] = xin[c & 1][g];
-              float v[16];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 b = *reinterpret_cast<const float4*>(sbias + nl + g * 16 + q * 4);
-                v[q * 4 + 0] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 0]), alpha, b.x);
-                v[q * 4 + 1] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 1]), alpha, b.y);
-                v[q * 4 + 2] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 2]), alpha, b.z);
-                v[q * 4 + 3] = fmaf(__uint_as_float(r[g * 16 + q * 4 + 3]), alpha, b.w);
-              }
-              if (n < scale_cols) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] *= col_scale;
-                if (n + 8 < scale_cols) {
-#pragma unroll
-                  for (int i = 8; i < 16; ++i) v[i] *= col_scale;
-                }
-              }
-              if (act == XP_ACT_QUICK_GELU) {
-                if (aux_p != nullptr) st_bf16x16(aux_p + a_off + n, full, second, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = quick_gelu(v[i]);
-              } else if (act == XP_ACT_DQUICK_GELU) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  v[2 * i] *= quick_gelu_grad(bf16_lo(xg[i]));
-                  v[2 * i + 1] *= quick_gelu_grad(bf16_hi(xg[i]));
-                }
-              } else if (act == XP_ACT_GELU_ERF) {
-                if (aux_p != nullptr) st_bf16x16(aux_p + a_off + n, full, second, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = act_gelu_erf(v[i]);
-              } else if (act == XP_ACT_DGELU_ERF) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  v[2 * i] *= act_gelu_erf_grad(bf16_lo(xg[i]));
-                  v[2 * i + 1] *= act_gelu_erf_grad(bf16_hi(xg[i]));
-                }
-              } else if (xin_p != nullptr) {   // residual add (never combined with a dGELU epilogue)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  v[2 * i] += bf16_lo(xg[i]);
-                  v[2 * i + 1] += bf16_hi(xg[i]);
-                }
-              }
-              if (OUT == XP_OUT_BF16) {
-                st_bf16x16(static_cast<__nv_bfloat16*>(p.c) + c_off + n, full, second, v);
-              } else if (OUT == XP_OUT_F32) {
-                float* dst = static_cast<float*>(p.c) + c_off + n;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  if (q < 2 || second)
-                    *reinterpret_cast<float4*>(dst + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-              } else {
-                float* dst = static_cast<float*>(p.c) + c_off + n;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  if (q < 2 || second)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(v[q * 4]),
-                                 "f"(v[q * 4 + 1]), "f"(v[q * 4 + 2]), "f"(v[q * 4 + 3])
-                                 : "memory");
-              }
-            }
-          }
-        }
-      }
+#include "gemm_epilogue.inc"
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
@@ -412,6 +301,54 @@ static int dispatch_out(const XpGemm* g, const CUtensorMap& tmA, const CUtensorM
   return fail("xp_gemm: bad out mode");
 }
 
+#include "gemm_pair.inc"
+
+template <int A_MN, int B_MN, int OUT>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev, int clusters,
+                       cudaStream_t stream) {
+  auto kern = gemm_pair_kernel<A_MN, B_MN, OUT>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    XP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = PAIR_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, dev));
+  XP_CHECK_LAUNCH("gemm_pair_kernel");
+  return 0;
+}
+
+template <int OUT>
+static int dispatch_pair_layout(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev,
+                                int clusters, cudaStream_t stream) {
+  if (g->a_layout == 0 && g->b_layout == 0) return launch_pair<0, 0, OUT>(tmA, tmB, dev, clusters, stream);
+  if (g->a_layout == 0 && g->b_layout == 1) return launch_pair<0, 1, OUT>(tmA, tmB, dev, clusters, stream);
+  if (g->a_layout == 1 && g->b_layout == 1) return launch_pair<1, 1, OUT>(tmA, tmB, dev, clusters, stream);
+  if (g->a_layout == 1 && g->b_layout == 0) return launch_pair<1, 0, OUT>(tmA, tmB, dev, clusters, stream);
+  return fail("xp_gemm: a_layout/b_layout must be 0 or 1");
+}
+
+static int dispatch_pair(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev,
+                         int clusters, cudaStream_t stream) {
+  switch (g->out) {
+    case XP_OUT_BF16: return dispatch_pair_layout<XP_OUT_BF16>(g, tmA, tmB, dev, clusters, stream);
+    case XP_OUT_F32: return dispatch_pair_layout<XP_OUT_F32>(g, tmA, tmB, dev, clusters, stream);
+    case XP_OUT_F32_ATOMIC: return dispatch_pair_layout<XP_OUT_F32_ATOMIC>(g, tmA, tmB, dev, clusters, stream);
+  }
+  return fail("xp_gemm: bad out mode");
+}
+
 static int g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0;
 }  // namespace xp
 
@@ -452,8 +389,15 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
     bn = (g->N >= 256 && tiles256 >= nsm) ? 256 : 128;
   }
   if (bn != 128 && bn != 256) return fail("xp_gemm: block_n must be 0, 128 or 256");
-  const long long total = static_cast<long long>(num_m) * ((g->N + bn - 1) / bn) * splits;
+  // 2-CTA pairs (256 x 256 tiles, UMMA M = 256) whenever the problem is big enough; cta_pair: 0 auto, 1 never, 2 force
+  bool pair = g->cta_pair == 2 || (g->cta_pair == 0 && g->block_n != 128 && g->N >= 256 && g->M >= 256);
+  if (g->cta_pair < 0 || g->cta_pair > 2) return fail("xp_gemm: cta_pair must be 0, 1 or 2");
+  if (pair) bn = 256;
+  const long long total = pair ? static_cast<long long>((g->M + 2 * BM - 1) / (2 * BM)) * ((g->N + 255) / 256) * splits
+                               : static_cast<long long>(num_m) * ((g->N + bn - 1) / bn) * splits;
   int grid = g->max_ctas > 0 ? g->max_ctas : nsm;
+  if (pair) grid /= 2;   // clusters
+  if (grid < 1) grid = 1;
   if (grid > total) grid = static_cast<int>(total);
 
   CUtensorMap tmA, tmB;
@@ -464,7 +408,7 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
     rc = make_tmap_bf16_2d(&tmA, g->a, g->M, g->K, g->lda, 64, BK);
   if (rc) return rc;
   if (g->b_layout == 0)
-    rc = make_tmap_bf16_2d(&tmB, g->b, g->K, g->N, g->ldb, BK, bn);
+    rc = make_tmap_bf16_2d(&tmB, g->b, g->K, g->N, g->ldb, BK, pair ? 128 : bn);   // a pair CTA stages half of B
   else
     rc = make_tmap_bf16_2d(&tmB, g->b, g->N, g->K, g->ldb, 64, BK);
   if (rc) return rc;
@@ -497,6 +441,7 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
   dev.mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : BK * 128;
   dev.mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024;
 
+  if (pair) return dispatch_pair(g, tmA, tmB, dev, grid, stream);
   return bn == 256 ? dispatch_out<256>(g, tmA, tmB, dev, grid, stream)
                    : dispatch_out<128>(g, tmA, tmB, dev, grid, stream);
 }

@@ -257,7 +257,7 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
             }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16_fma(pv[2 * i], pv[2 * i + 1]);
+          for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
           // chunk c+1 (columns [16c+16, 16c+32)) is already in flight; P goes to columns [8c, 8c+8) < 16c+16
           tmem_st8(t_lane + c * 8, pk);
         }

@@ -39,7 +39,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          residual: Optional[torch.Tensor] = None, ldr: int = 0, aux: Optional[torch.Tensor] = None, ld_aux: int = 0,
          act: int = _lib.ACT_NONE, out_mode: int = _lib.OUT_BF16, splits: int = 1, scale_cols: int = 0,
          col_scale: float = 1.0, alpha: float = 1.0, c_group: int = 0, c_group_stride: int = 0, r_group: int = 0,
-         r_group_stride: int = 0, block_n: int = 0, a_offset: int = 0, b_offset: int = 0, c_offset: int = 0) -> None:
+         r_group_stride: int = 0, block_n: int = 0, a_offset: int = 0, b_offset: int = 0, c_offset: int = 0,
+         cta_pair: int = 0) -> None:
     """out = epilogue(alpha * A @ B^T); offsets are in elements from the tensors' data pointers."""
     assert a.dtype == bf16 and b.dtype == bf16
     if bias is not None:
@@ -56,7 +57,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.a_layout, g.b_layout, g.act, g.out = a_layout, b_layout, act, out_mode
     g.splits, g.scale_cols, g.alpha, g.col_scale = splits, scale_cols, alpha, col_scale
     g.c_group, g.c_group_stride, g.r_group, g.r_group_stride = c_group, c_group_stride, r_group, r_group_stride
-    g.block_n, g.max_ctas = block_n, 0
+    g.block_n, g.max_ctas, g.cta_pair = block_n, 0, cta_pair
     if _gemm_timer is None:
         check(lib().xp_gemm(C.byref(g), _stream()), "xp_gemm")
     else:  # bench.py's roofline leg: CUDA events on the launching stream around this launch
@@ -91,16 +92,20 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, **kw) -> N
 
 
 def wgrad_plan(n_out: int, n_in: int, rows: int, sms: int = 148):
-    """(block_n, splits) for a weight-gradient GEMM: 256-wide tiles (96 B/clk/SM of operand traffic instead of
-    128) and the split-K factor that fills whole waves of the persistent grid."""
+    """(block_n, splits) for a weight-gradient GEMM: the split-K factor that fills whole waves of the persistent grid.
+    Outputs of at least 256 x 256 run on CTA pairs (256 x 256 tiles, sms/2 clusters), smaller ones on single CTAs."""
+    pair = n_out >= 256 and n_in >= 256
     bn = 256 if n_in >= 256 else 128
-    tiles = ((n_out + 127) // 128) * ((n_in + bn - 1) // bn)
+    if pair:
+        tiles, slots = ((n_out + 255) // 256) * ((n_in + 255) // 256), sms // 2
+    else:
+        tiles, slots = ((n_out + 127) // 128) * ((n_in + bn - 1) // bn), sms
     best, best_eff = 1, 0.0
-    for s in range(1, 17):
+    for s in range(1, 33):
         if s > 1 and rows // s < 1024:
             break
         total = tiles * s
-        eff = total / (((total + sms - 1) // sms) * sms)
+        eff = total / (((total + slots - 1) // slots) * slots)
         if eff > best_eff + 0.02:
             best, best_eff = s, eff
     return bn, best
