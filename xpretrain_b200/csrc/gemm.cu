@@ -85,7 +85,7 @@ __device__ __forceinline__ void st_bf16x16(__nv_bfloat16* ptr, bool wide, bool s
   }
 }
 
-template <int BN, int A_MN, int B_MN, int OUT>
+template <int BN, int A_MN, int B_MN, int OUT, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   using Cfg = GemmCfg<BN>;
@@ -225,7 +225,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // kernel parameters used per element live in registers (the asm "memory" clobbers would otherwise force
     // ptxas to re-read them from the constant bank inside the loops)
     const bool wide = p.wide != 0;       // every bf16 row segment is 32-byte aligned -> 256-bit accesses
-    const int act = p.act, N = p.N, scale_cols = p.scale_cols;
+    constexpr int act = ACT;             // compile-time: the unused activation branches are not even generated
+    const int N = p.N, scale_cols = p.scale_cols;
     const float alpha = p.alpha, col_scale = p.col_scale;
     __nv_bfloat16* const aux_p = p.aux;
     const bool need_aux_in = (act == XP_ACT_DQUICK_GELU || act == XP_ACT_DGELU_ERF);
@@ -265,11 +266,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN, int A_MN, int B_MN, int OUT>
+template <int BN, int A_MN, int B_MN, int OUT, int ACT>
 static int launch_gemm(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev, int grid,
                        cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, OUT, ACT>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     XP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -280,33 +281,47 @@ static int launch_gemm(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMa
   return 0;
 }
 
-template <int BN, int OUT>
+template <int BN, int OUT, int ACT>
 static int dispatch_layout(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev,
                            int grid, cudaStream_t stream) {
-  if (g->a_layout == 0 && g->b_layout == 0) return launch_gemm<BN, 0, 0, OUT>(g, tmA, tmB, dev, grid, stream);
-  if (g->a_layout == 0 && g->b_layout == 1) return launch_gemm<BN, 0, 1, OUT>(g, tmA, tmB, dev, grid, stream);
-  if (g->a_layout == 1 && g->b_layout == 1) return launch_gemm<BN, 1, 1, OUT>(g, tmA, tmB, dev, grid, stream);
-  if (g->a_layout == 1 && g->b_layout == 0) return launch_gemm<BN, 1, 0, OUT>(g, tmA, tmB, dev, grid, stream);
+  if (g->a_layout == 0 && g->b_layout == 0) return launch_gemm<BN, 0, 0, OUT, ACT>(g, tmA, tmB, dev, grid, stream);
+  if (g->a_layout == 0 && g->b_layout == 1) return launch_gemm<BN, 0, 1, OUT, ACT>(g, tmA, tmB, dev, grid, stream);
+  if (g->a_layout == 1 && g->b_layout == 1) return launch_gemm<BN, 1, 1, OUT, ACT>(g, tmA, tmB, dev, grid, stream);
+  if (g->a_layout == 1 && g->b_layout == 0) return launch_gemm<BN, 1, 0, OUT, ACT>(g, tmA, tmB, dev, grid, stream);
   return fail("xp_gemm: a_layout/b_layout must be 0 or 1");
+}
+
+// The activation epilogues exist for bf16 outputs only (forward activations / their gradients).
+template <int BN>
+static int dispatch_act_bf16(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev, int grid,
+                             cudaStream_t stream) {
+  switch (g->act) {
+    case XP_ACT_NONE: return dispatch_layout<BN, XP_OUT_BF16, XP_ACT_NONE>(g, tmA, tmB, dev, grid, stream);
+    case XP_ACT_QUICK_GELU: return dispatch_layout<BN, XP_OUT_BF16, XP_ACT_QUICK_GELU>(g, tmA, tmB, dev, grid, stream);
+    case XP_ACT_DQUICK_GELU: return dispatch_layout<BN, XP_OUT_BF16, XP_ACT_DQUICK_GELU>(g, tmA, tmB, dev, grid, stream);
+    case XP_ACT_GELU_ERF: return dispatch_layout<BN, XP_OUT_BF16, XP_ACT_GELU_ERF>(g, tmA, tmB, dev, grid, stream);
+    case XP_ACT_DGELU_ERF: return dispatch_layout<BN, XP_OUT_BF16, XP_ACT_DGELU_ERF>(g, tmA, tmB, dev, grid, stream);
+  }
+  return fail("xp_gemm: bad act");
 }
 
 template <int BN>
 static int dispatch_out(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev, int grid,
                         cudaStream_t stream) {
   switch (g->out) {
-    case XP_OUT_BF16: return dispatch_layout<BN, XP_OUT_BF16>(g, tmA, tmB, dev, grid, stream);
-    case XP_OUT_F32: return dispatch_layout<BN, XP_OUT_F32>(g, tmA, tmB, dev, grid, stream);
-    case XP_OUT_F32_ATOMIC: return dispatch_layout<BN, XP_OUT_F32_ATOMIC>(g, tmA, tmB, dev, grid, stream);
+    case XP_OUT_BF16: return dispatch_act_bf16<BN>(g, tmA, tmB, dev, grid, stream);
+    case XP_OUT_F32: return dispatch_layout<BN, XP_OUT_F32, XP_ACT_NONE>(g, tmA, tmB, dev, grid, stream);
+    case XP_OUT_F32_ATOMIC: return dispatch_layout<BN, XP_OUT_F32_ATOMIC, XP_ACT_NONE>(g, tmA, tmB, dev, grid, stream);
   }
   return fail("xp_gemm: bad out mode");
 }
 
 #include "gemm_pair.inc"
 
-template <int A_MN, int B_MN, int OUT>
+template <int A_MN, int B_MN, int OUT, int ACT>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev, int clusters,
                        cudaStream_t stream) {
-  auto kern = gemm_pair_kernel<A_MN, B_MN, OUT>;
+  auto kern = gemm_pair_kernel<A_MN, B_MN, OUT, ACT>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     XP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
@@ -329,22 +344,30 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return 0;
 }
 
-template <int OUT>
+template <int OUT, int ACT>
 static int dispatch_pair_layout(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev,
                                 int clusters, cudaStream_t stream) {
-  if (g->a_layout == 0 && g->b_layout == 0) return launch_pair<0, 0, OUT>(tmA, tmB, dev, clusters, stream);
-  if (g->a_layout == 0 && g->b_layout == 1) return launch_pair<0, 1, OUT>(tmA, tmB, dev, clusters, stream);
-  if (g->a_layout == 1 && g->b_layout == 1) return launch_pair<1, 1, OUT>(tmA, tmB, dev, clusters, stream);
-  if (g->a_layout == 1 && g->b_layout == 0) return launch_pair<1, 0, OUT>(tmA, tmB, dev, clusters, stream);
+  if (g->a_layout == 0 && g->b_layout == 0) return launch_pair<0, 0, OUT, ACT>(tmA, tmB, dev, clusters, stream);
+  if (g->a_layout == 0 && g->b_layout == 1) return launch_pair<0, 1, OUT, ACT>(tmA, tmB, dev, clusters, stream);
+  if (g->a_layout == 1 && g->b_layout == 1) return launch_pair<1, 1, OUT, ACT>(tmA, tmB, dev, clusters, stream);
+  if (g->a_layout == 1 && g->b_layout == 0) return launch_pair<1, 0, OUT, ACT>(tmA, tmB, dev, clusters, stream);
   return fail("xp_gemm: a_layout/b_layout must be 0 or 1");
 }
 
 static int dispatch_pair(const XpGemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev,
                          int clusters, cudaStream_t stream) {
   switch (g->out) {
-    case XP_OUT_BF16: return dispatch_pair_layout<XP_OUT_BF16>(g, tmA, tmB, dev, clusters, stream);
-    case XP_OUT_F32: return dispatch_pair_layout<XP_OUT_F32>(g, tmA, tmB, dev, clusters, stream);
-    case XP_OUT_F32_ATOMIC: return dispatch_pair_layout<XP_OUT_F32_ATOMIC>(g, tmA, tmB, dev, clusters, stream);
+    case XP_OUT_BF16:
+      switch (g->act) {
+        case XP_ACT_NONE: return dispatch_pair_layout<XP_OUT_BF16, XP_ACT_NONE>(g, tmA, tmB, dev, clusters, stream);
+        case XP_ACT_QUICK_GELU: return dispatch_pair_layout<XP_OUT_BF16, XP_ACT_QUICK_GELU>(g, tmA, tmB, dev, clusters, stream);
+        case XP_ACT_DQUICK_GELU: return dispatch_pair_layout<XP_OUT_BF16, XP_ACT_DQUICK_GELU>(g, tmA, tmB, dev, clusters, stream);
+        case XP_ACT_GELU_ERF: return dispatch_pair_layout<XP_OUT_BF16, XP_ACT_GELU_ERF>(g, tmA, tmB, dev, clusters, stream);
+        case XP_ACT_DGELU_ERF: return dispatch_pair_layout<XP_OUT_BF16, XP_ACT_DGELU_ERF>(g, tmA, tmB, dev, clusters, stream);
+      }
+      return fail("xp_gemm: bad act");
+    case XP_OUT_F32: return dispatch_pair_layout<XP_OUT_F32, XP_ACT_NONE>(g, tmA, tmB, dev, clusters, stream);
+    case XP_OUT_F32_ATOMIC: return dispatch_pair_layout<XP_OUT_F32_ATOMIC, XP_ACT_NONE>(g, tmA, tmB, dev, clusters, stream);
   }
   return fail("xp_gemm: bad out mode");
 }
@@ -370,6 +393,7 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
   if (splits > 1 && g->out != XP_OUT_F32_ATOMIC) return fail("xp_gemm: split-K requires XP_OUT_F32_ATOMIC");
   if ((g->act == XP_ACT_DQUICK_GELU || g->act == XP_ACT_DGELU_ERF) && !g->aux)
     return fail("xp_gemm: dGELU epilogue needs aux (the forward pre-activation)");
+  if (g->act != XP_ACT_NONE && g->out != XP_OUT_BF16) return fail("xp_gemm: activation epilogues need a bf16 output");
   if ((g->act == XP_ACT_DQUICK_GELU || g->act == XP_ACT_DGELU_ERF) && g->residual)
     return fail("xp_gemm: a dGELU epilogue cannot be combined with a residual add");
   const int elem_c = g->out == XP_OUT_BF16 ? 2 : 4;
