@@ -2,8 +2,8 @@
 //   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring
 //   -> tcgen05.mma (single issuing thread, fp32 accumulators in TMEM, double buffered)
 //   -> tcgen05.ld epilogue (bias / q-scale / QuickGELU / dQuickGELU / residual) -> global.
-// One CTA per SM, 18 warps: warp0 = TMA producer, warp1 = TMEM allocator + MMA issuer,
-// warps 2..17 = epilogue (four warps per TMEM lane quarter, each taking a quarter of the columns).
+// One CTA per SM, 12 warps: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+// warps 4..11 = epilogue (two warps per TMEM lane quarter, each taking half of the columns).
 //
 // Replaces (see include/xpretrain_b200.h) every nn.Linear forward/backward on
 // the CLIP-ViP hot path: CLIP_ViP.py:341-343,379,393-395,1141-1145 and the
@@ -17,8 +17,8 @@ namespace xp {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 576;  // 2 control warps + 16 epilogue warps
-constexpr int EPI_THREADS = 512;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
 
 struct GemmDev {
   void* c;
@@ -125,7 +125,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 2) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -214,13 +214,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 4) {
     // ---------------------------------------------------------- epilogue
-    // 16 warps: warp w owns TMEM lane quarter w % 4 (the quarter the hardware lets it read) and column quarter
-    // (w - 2) / 4 of every accumulator.
-    const int quarter = warp & 3;
-    const int colq = (warp - 2) >> 2;
-    const int etid = threadIdx.x - 64;   // 0..511
+    // 8 warps: warp (4+e) owns TMEM lane quarter e&3 and column half e>>2 of every accumulator.
+    const int ew = warp - 4;
+    const int quarter = ew & 3;  // == warp % 4, the lane quarter this warp may read
+    const int half = ew >> 2;
+    const int etid = threadIdx.x - 128;  // 0..255
+    constexpr int CHUNKS = BN / 64;      // 32-column chunks per warp per tile
     // kernel parameters used per element live in registers (the asm "memory" clobbers would otherwise force
     // ptxas to re-read them from the constant bank inside the loops)
     const bool wide = p.wide != 0;       // every bf16 row segment is 32-byte aligned -> 256-bit accesses
@@ -259,7 +260,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
