@@ -183,7 +183,7 @@ def vision_tower(sd: Dict[str, Tensor], video: Tensor, cfg: ClipVipCfg, return_h
 def text_additive_mask(attention_mask: Tensor, dtype: torch.dtype) -> Tensor:
     """Causal (-inf above the diagonal, CLIP_ViP.py:788-797) + padding (finfo.min on masked keys, :50-61,760)."""
     B, S = attention_mask.shape
-    causal = torch.full((S, S), float("-inf"), dtype=dtype).triu(1)
+    causal = torch.full((S, S), float("-inf"), dtype=dtype, device=attention_mask.device).triu(1)
     inv = 1.0 - attention_mask[:, None, None, :].to(dtype)
     pad = inv.masked_fill(inv.bool(), torch.finfo(dtype).min).expand(B, 1, S, S)
     return causal[None, None] + pad
@@ -202,7 +202,7 @@ def text_tower(sd: Dict[str, Tensor], input_ids: Tensor, attention_mask: Tensor,
         hidden.append(x)
     x = layer_norm(x, sd, "text_model.final_layer_norm", cfg.ln_eps)
     # EOS pooling: FIRST index of the maximum token id (CLIP_ViP.py:776; pad id == eos id 49407)
-    pooled = x[torch.arange(B), input_ids.argmax(dim=-1)]
+    pooled = x[torch.arange(B, device=x.device), input_ids.argmax(dim=-1)]
     return (pooled, hidden) if return_hidden else pooled
 
 
