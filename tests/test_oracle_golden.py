@@ -98,3 +98,42 @@ def test_flop_model_matches_baseline_md():
     assert abs(f["fwd"] / 1e9 - 423.12) < 0.05
     assert abs(f["train"] / 1e9 - 1266.58) < 0.2
     assert abs(f["vip_block_fwd"] / 1e9 - 34.825) < 0.01
+
+
+# ------------------------------------------------------------------ config #4: HD-VILA TimeSformer
+def _tsf_replay(gold):
+    from oracle import timesformer_oracle as TO
+
+    cfg = TO.TimeSformerCfg(**gold["cfg"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in TO.init_state_dict(cfg, seed=gold["weight_seed"]).items()}
+    x = TO.synthetic_input(gold["B"], gold["T"], gold["H"], gold["W"], cfg, seed=gold["data_seed"]).requires_grad_(True)
+    g = torch.Generator().manual_seed(gold["data_seed"] + 1)
+    w_out = torch.randn(gold["out"].shape, generator=g) / (gold["B"] * gold["T"] * gold["H"] * gold["W"]) ** 0.5
+    return TO, cfg, sd, x, w_out
+
+
+@pytest.mark.parametrize("name", ["timesformer_interp_b2", "timesformer_native_b2"])
+def test_timesformer_oracle_replays_reference_golden(golden_dir, name):
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    TO, cfg, sd, x, w_out = _tsf_replay(gold)
+    out, hidden = TO.timesformer_forward(sd, x, cfg, return_hidden=True)
+    assert out.shape == gold["out"].shape
+    assert _rel(out.detach(), gold["out"]) < 1e-5
+    assert _rel(torch.stack([h[:, :6].detach() for h in hidden]), gold["hidden_rows"]) < 1e-5
+    loss = (out * w_out).sum()
+    assert abs(float(loss) - float(gold["loss"])) < 1e-5 * max(1.0, abs(float(gold["loss"])))
+    loss.backward()
+    assert _rel(x.grad[:, 0], gold["dx_t0"]) < 1e-4
+    for n, ref in gold["grads"].items():
+        got = sd[n].grad[:8] if ref.dim() == 2 else sd[n].grad
+        assert float((got - ref).norm()) < 1e-4 * gold["grad_norms"][n] + 1e-9, n
+    assert sd["norm.weight"].grad is None      # constructed but never applied (timesformer.py:451)
+
+
+def test_timesformer_flop_model_matches_baseline_md():
+    from oracle import timesformer_oracle as TO
+
+    cfg = TO.TimeSformerCfg()
+    assert abs(TO.flops_per_sample(cfg, 7, 10, 16) / 1e9 - 162.78) < 0.01
+    assert abs(TO.flops_per_sample(cfg, 8, 7, 7) / 1e9 - 56.27) < 0.01
+    assert abs(TO.flops_per_sample(cfg, 8, 28, 28) / 1e9 - 975.81) < 0.01
