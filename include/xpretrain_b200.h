@@ -181,6 +181,39 @@ int xp_nce_split(const float* x, void* x3_bf16, void* hi_bf16, int32_t rows, int
 int xp_nce_softmax_grad(const float* z, const float* logit_scale, float* lse_rows, float* lse_cols, void* g_scaled_bf16,
                         float* loss, float* d_logit_scale, int32_t N, int64_t ld, void* stream);
 
+/* ---- BASELINE.json config #4: HD-VILA TimeSformer (divided space-time attention), hd-vila/src/modeling/timesformer.py
+ *
+ * xp_seg_attention_{fwd,bwd}: multi-head attention (head_dim 64) over strided "sequences" of a token-major fused
+ * [n_rows, ld_qkv] bf16 buffer (columns [q|k|v], head h at h*64; q pre-scaled by head_dim**-0.5).  Replaces
+ * Attention.forward (timesformer.py:156-173) TOGETHER WITH the einops rearranges around it (Block.forward :210-219):
+ *   sequence s starts at row (s / inner) * outer_stride + (s % inner) * inner_stride, its tokens are tok_stride rows
+ *   apart, it has min(seq_len, rows that fit) tokens, and token i attends to token j iff i / seg_len == j / seg_len
+ *   (seg_len >= seq_len: dense).
+ *   temporal ('(b h w) t m'):  G = 64 / T groups per sequence: seq_len = G*T, seg_len = T, inner = 1,
+ *                              outer_stride = G*T, tok_stride = 1, n_seq = ceil(n_rows / (G*T))
+ *   spatial  ('(b t) (h w) m'): seq_len = seg_len = H*W, inner = T, outer_stride = H*W*T, inner_stride = 1,
+ *                              tok_stride = T, n_seq = B*T
+ * out: [n_rows, ld_out] bf16 (same row order as qkv); lse, delta: [heads, n_rows] fp32 (delta is scratch written by bwd);
+ * dqkv: [n_rows, ld_qkv] bf16, every (row, head) slice covered by a sequence is overwritten; dq is multiplied by q_scale. */
+typedef struct XpSegAttn {
+  int64_t n_rows;
+  int64_t ld_qkv, ld_out;
+  int64_t outer_stride, inner_stride, tok_stride;
+  int32_t heads, n_seq, seq_len, seg_len, inner, reserved;
+} XpSegAttn;
+int xp_seg_attention_fwd(const void* qkv, void* out, float* lse, const XpSegAttn* desc, void* stream);
+int xp_seg_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                         const XpSegAttn* desc, float q_scale, void* stream);
+
+/* Token assembly, TimeSformer.forward timesformer.py:481-509: x [B,T,C,H*W] (XP_DTYPE_*) -> tokens bf16 [(b, p, t), C]
+ * (rows in the reference's (h w t) order) = x[b,t,:,p] + pos[p,:] + time[t,:]; pos [H*W, C] / time [T, C] fp32 are the
+ * (already interpolated) tables, NULL = no table (plain tokenisation, used for the output gradient).
+ * xp_tsf_untokenize is the inverse layout change (tokens -> [B,T,C,H*W]): the module output (:523) and d(x). */
+int xp_tsf_embed_fwd(const void* x, int32_t x_dtype, const float* pos, const float* time, void* tokens_bf16, int32_t B,
+                     int32_t T, int32_t C, int32_t HW, void* stream);
+int xp_tsf_untokenize(const void* tokens_bf16, void* x, int32_t x_dtype, int32_t B, int32_t T, int32_t C, int32_t HW,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

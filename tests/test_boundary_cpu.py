@@ -68,3 +68,23 @@ def test_wgrad_plan_fills_waves():
         bn, s = wgrad_plan(n_out, n_in, 150784)
         tiles = ((n_out + 255) // 256) * ((n_in + 255) // 256) * s        # CTA pairs: 256 x 256 tiles on 74 clusters
         assert tiles / (-(-tiles // 74) * 74) > 0.9
+
+
+def test_timesformer_module_has_the_reference_state_dict():
+    """config #4 drop-in: parameter names/shapes of hd-vila/src/modeling/timesformer.py:421-455 (no kernel is called)."""
+    from oracle import timesformer_oracle as TO
+    from xpretrain_b200.modeling.timesformer import TimeSformer
+
+    cfg = TO.TimeSformerCfg(depth=2, num_frames=7, H=10, W=16, embed_dim=128, num_heads=2)
+    m = TimeSformer(depth=2, num_frames=7, H=10, W=16, embed_dim=128, num_heads=2)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == TO.param_shapes(cfg)
+    m.load_state_dict(TO.init_state_dict(cfg, seed=0), strict=True)
+    # reference init quirks (timesformer.py:457-464): temporal_fc of every block but the first starts at zero
+    m2 = TimeSformer(depth=2, embed_dim=128, num_heads=2)
+    assert float(m2.blocks[1].temporal_fc.weight.abs().sum()) == 0.0
+    assert float(m2.blocks[0].temporal_fc.weight.abs().sum()) > 0.0
+    import pytest
+    import torch
+    with pytest.raises(Exception):          # no CPU path
+        m(torch.zeros(1, 7, 128, 10, 16))

@@ -31,6 +31,12 @@ class XpRowMap(C.Structure):
     _fields_ = [("group", c_i64), ("group_stride", c_i64), ("ld", c_i64), ("offsets", c_void_p)]
 
 
+class XpSegAttn(C.Structure):
+    _fields_ = [("n_rows", c_i64), ("ld_qkv", c_i64), ("ld_out", c_i64), ("outer_stride", c_i64), ("inner_stride", c_i64),
+                ("tok_stride", c_i64), ("heads", c_int), ("n_seq", c_int), ("seq_len", c_int), ("seg_len", c_int),
+                ("inner", c_int), ("reserved", c_int)]
+
+
 ACT_NONE, ACT_QUICK_GELU, ACT_DQUICK_GELU, ACT_GELU_ERF, ACT_DGELU_ERF = 0, 1, 2, 3, 4
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
@@ -79,6 +85,11 @@ SIGNATURES = {
     "xp_nce_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "xp_nce_softmax_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_i64, c_void_p]),
+    "xp_seg_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, P(XpSegAttn), c_void_p]),
+    "xp_seg_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(XpSegAttn), c_float,
+                                     c_void_p]),
+    "xp_tsf_embed_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "xp_tsf_untokenize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,301 @@
+"""HD-VILA's TimeSformer (divided space-time attention) on the B200 kernels — BASELINE.json config #4.
+
+Drop-in for `TimeSformer` of /root/reference/hd-vila/src/modeling/timesformer.py:421-525 as `HDVILA.__init__` builds it
+(e2e_model.py:53-55): same constructor arguments, same `state_dict()` names and shapes (`pos_embed`, `time_embed`,
+`blocks.N.{norm1,attn.qkv,attn.proj,temporal_norm1,temporal_attn.qkv,temporal_attn.proj,temporal_fc,norm2,mlp.fc1,
+mlp.fc2}`, and the never-applied `norm`), same `forward(x[B,T,C,H,W]) -> [B,T,C,H,W]`.
+
+The module tree only holds parameters.  forward/backward run as ONE autograd.Function over token-major bf16 matrices
+`[B*H*W*T, C]` in the reference's `(h w t)` row order:
+  * every Linear is the tcgen05 GEMM (`xp_gemm`) with bias / q-scale / erf-GELU / residual epilogues,
+  * both attentions are `xp_seg_attention_*` reading the fused qkv buffer through strides — the six einops rearranges
+    per block of timesformer.py:210-219 never materialise,
+  * LayerNorm fwd/bwd are the row kernels shared with CLIP-ViP.
+There is no CPU path.  Stochastic depth (DropPath, timesformer.py:98-121) is NOT implemented yet: training-mode
+forward with drop_path_rate > 0 raises instead of silently changing the regulariser (eval mode is exact).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib, ops
+from .clip_vip import _alloc_flat
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+class _TsfAttention(nn.Module):
+    def __init__(self, dim: int, qkv_bias: bool):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)     # timesformer.py:151
+        self.proj = nn.Linear(dim, dim)
+
+
+class _TsfMlp(nn.Module):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _TsfBlock(nn.Module):
+    def __init__(self, dim: int, hidden: int, qkv_bias: bool, eps: float):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=eps)
+        self.attn = _TsfAttention(dim, qkv_bias)
+        self.temporal_norm1 = nn.LayerNorm(dim, eps=eps)
+        self.temporal_attn = _TsfAttention(dim, qkv_bias)
+        self.temporal_fc = nn.Linear(dim, dim)
+        self.norm2 = nn.LayerNorm(dim, eps=eps)
+        self.mlp = _TsfMlp(dim, hidden)
+
+
+class TimeSformer(nn.Module):
+    """Constructor mirrors timesformer.py:424-427 (only the arguments HD-VILA uses change behaviour)."""
+
+    def __init__(self, depth=12, num_frames=7, H=10, W=16, embed_dim=768, num_heads=12, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1, norm_layer=None,
+                 attention_type='divided_space_time', timesformer_type='new', dropout=0.):
+        super().__init__()
+        if attention_type != 'divided_space_time':
+            raise NotImplementedError("only attention_type='divided_space_time' (the one HD-VILA uses) is built")
+        if embed_dim != num_heads * 64:
+            raise ValueError("the B200 attention kernels are built for head_dim 64 (embed_dim == 64 * num_heads)")
+        if qk_scale is not None or drop_rate or attn_drop_rate or dropout or not qkv_bias:
+            raise NotImplementedError("qk_scale / dropout / qkv_bias=False are not used by HD-VILA and are not built")
+        self.depth, self.H, self.W, self.embed_dim, self.num_heads = depth, H, W, embed_dim, num_heads
+        self.num_features = embed_dim
+        self.attention_type, self.timesformer_type = attention_type, timesformer_type
+        self.drop_path_rate = float(drop_path_rate)
+        self.eps = 1e-6 if norm_layer is None else getattr(norm_layer, "keywords", {}).get("eps", 1e-5)
+        self.pos_embed = nn.Parameter(torch.zeros(1, H * W, embed_dim))
+        self.time_embed = nn.Parameter(torch.zeros(1, num_frames, embed_dim))
+        hidden = int(embed_dim * mlp_ratio)
+        self.blocks = nn.ModuleList([_TsfBlock(embed_dim, hidden, qkv_bias, self.eps) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=self.eps)   # constructed, never applied (timesformer.py:451)
+        self._cache: Dict[str, list] = {}
+        self._init_weights()
+
+    def _init_weights(self):
+        """timesformer.py:453-473: trunc_normal(0.02) weights, zero biases, unit LayerNorms, temporal_fc of blocks > 0 zeroed."""
+        nn.init.trunc_normal_(self.pos_embed, std=.02)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=.02)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+        for i, blk in enumerate(self.blocks):
+            if i > 0:
+                nn.init.zeros_(blk.temporal_fc.weight)
+                nn.init.zeros_(blk.temporal_fc.bias)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'pos_embed', 'time_embed'}
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise _lib.XpError("xpretrain_b200 TimeSformer needs CUDA tensors on a B200: there is no CPU path")
+        if self.training and self.drop_path_rate > 0 and torch.is_grad_enabled():
+            raise NotImplementedError("stochastic depth (DropPath) is not implemented: build with drop_path_rate=0 "
+                                      "or call .eval()")
+        names, params = zip(*[(n, p) for n, p in self.named_parameters() if not n.startswith("norm.")])
+        return _TimeSformerFunction.apply(self, list(names), x, *params)
+
+
+# ----------------------------------------------------------------------------------- helpers
+def _w(model: TimeSformer, name: str, p: torch.Tensor) -> torch.Tensor:
+    """bf16 compute copy of a GEMM weight, refreshed when the fp32 master's version counter moves."""
+    ent = model._cache.get(name)
+    if ent is None or ent[0].device != p.device:
+        ent = [torch.empty(p.shape, dtype=bf16, device=p.device), None]
+        model._cache[name] = ent
+    if ent[1] != p._version:
+        ops.cast_bf16(p.detach().contiguous(), ent[0])
+        ent[1] = p._version
+    return ent[0]
+
+
+def _tables(model: TimeSformer, T: int, H: int, W: int, pos_param=None, time_param=None):
+    """pos [H*W, C] / time [T, C] fp32 as the forward adds them: bilinear / linear interpolation of the learned tables
+    when the grid or the frame count differs (timesformer.py:487-494, 504-508).  Parameter preprocessing on tiny
+    tensors (torch); with `pos_param`/`time_param` given it is differentiable (used to pull table gradients back)."""
+    C_ = model.embed_dim
+    pos = model.pos_embed.detach() if pos_param is None else pos_param
+    time = model.time_embed.detach() if time_param is None else time_param
+    if H != model.H or W != model.W:
+        grid = pos[0].unsqueeze(0).transpose(1, 2).reshape(1, C_, model.H, model.W)
+        pos = F.interpolate(grid, size=(H, W), mode='bilinear').flatten(2).transpose(1, 2)
+    if T != time.shape[1]:
+        time = F.interpolate(time.transpose(1, 2), size=T, mode='linear').transpose(1, 2)
+    return pos[0].float().contiguous(), time[0].float().contiguous()
+
+
+def _ln(x, ln: nn.LayerNorm, rows: int, C_: int, eps: float):
+    plain = ops.rowmap(C_)
+    mean = torch.empty(rows, dtype=f32, device=x.device)
+    rstd = torch.empty_like(mean)
+    y = torch.empty(rows, C_, dtype=bf16, device=x.device)
+    ops.layernorm_fwd(x, plain, y, plain, ln.weight, ln.bias, mean, rstd, rows, C_, eps)
+    return y, mean, rstd
+
+
+def _attn_fwd(model, pre: str, att: _TsfAttention, h, desc, rows: int, C_: int):
+    dev = h.device
+    qkv = torch.empty(rows, 3 * C_, dtype=bf16, device=dev)
+    # (q k^T) * head_dim**-0.5 (timesformer.py:165): 0.125 is a power of two, folding it into q (bias included) is exact
+    ops.linear_fwd(h, _w(model, pre + "qkv.weight", att.qkv.weight), att.qkv.bias, qkv, scale_cols=C_, col_scale=0.125)
+    a = torch.empty(rows, C_, dtype=bf16, device=dev)
+    lse = torch.empty(model.num_heads, rows, dtype=f32, device=dev)
+    ops.seg_attention_fwd(qkv, a, lse, desc)
+    return qkv, a, lse
+
+
+def _block_fwd(model: TimeSformer, i: int, x, descs, rows: int, save: bool):
+    """timesformer.py:207-226.  x: [rows, C] bf16 tokens, (h w t) order."""
+    blk = model.blocks[i]
+    C_, I = model.embed_dim, blk.mlp.fc1.weight.shape[0]
+    dev, p = x.device, f"blocks.{i}."
+    d_t, d_s = descs
+    # ---- temporal attention -> proj -> temporal_fc -> residual (:209-214)
+    ln_t, mean_t, rstd_t = _ln(x, blk.temporal_norm1, rows, C_, model.eps)
+    qkv_t, a_t, lse_t = _attn_fwd(model, p + "temporal_attn.", blk.temporal_attn, ln_t, d_t, rows, C_)
+    p_t = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.linear_fwd(a_t, _w(model, p + "temporal_attn.proj.weight", blk.temporal_attn.proj.weight),
+                   blk.temporal_attn.proj.bias, p_t)
+    xt = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.linear_fwd(p_t, _w(model, p + "temporal_fc.weight", blk.temporal_fc.weight), blk.temporal_fc.bias, xt,
+                   residual=x, ldr=C_)
+    # ---- spatial attention -> proj -> residual (:216-224)
+    ln_s, mean_s, rstd_s = _ln(xt, blk.norm1, rows, C_, model.eps)
+    qkv_s, a_s, lse_s = _attn_fwd(model, p + "attn.", blk.attn, ln_s, d_s, rows, C_)
+    x2 = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.linear_fwd(a_s, _w(model, p + "attn.proj.weight", blk.attn.proj.weight), blk.attn.proj.bias, x2,
+                   residual=xt, ldr=C_)
+    # ---- MLP with exact-erf GELU (:225, :132-138)
+    ln_m, mean_m, rstd_m = _ln(x2, blk.norm2, rows, C_, model.eps)
+    pre = torch.empty(rows, I, dtype=bf16, device=dev) if save else None
+    f1 = torch.empty(rows, I, dtype=bf16, device=dev)
+    ops.linear_fwd(ln_m, _w(model, p + "mlp.fc1.weight", blk.mlp.fc1.weight), blk.mlp.fc1.bias, f1,
+                   act=_lib.ACT_GELU_ERF, aux=pre, ld_aux=I)
+    out = torch.empty(rows, C_, dtype=bf16, device=dev)
+    ops.linear_fwd(f1, _w(model, p + "mlp.fc2.weight", blk.mlp.fc2.weight), blk.mlp.fc2.bias, out, residual=x2, ldr=C_)
+    saved = (x, mean_t, rstd_t, ln_t, qkv_t, a_t, lse_t, p_t, xt, mean_s, rstd_s, ln_s, qkv_s, a_s, lse_s, x2, mean_m,
+             rstd_m, ln_m, pre, f1) if save else None
+    return out, saved
+
+
+def _linear_bwd(model, name: str, lin: nn.Linear, dy, x_in, grads, need_dx: bool = True, **dgrad_kw):
+    """dW += dy^T x_in, db += colsum(dy), returns dx = dy W (bf16)."""
+    ops.linear_wgrad(dy, x_in, grads[name + ".weight"])
+    ops.colsum(dy, grads[name + ".bias"])
+    if not need_dx:
+        return None
+    dx = torch.empty(dy.shape[0], lin.weight.shape[1], dtype=bf16, device=dy.device)
+    ops.linear_dgrad(dy, _w(model, name + ".weight", lin.weight), dx, **dgrad_kw)
+    return dx
+
+
+def _block_bwd(model: TimeSformer, i: int, dx, saved, descs, grads, rows: int):
+    (x, mean_t, rstd_t, ln_t, qkv_t, a_t, lse_t, p_t, xt, mean_s, rstd_s, ln_s, qkv_s, a_s, lse_s, x2, mean_m, rstd_m,
+     ln_m, pre, f1) = saved
+    blk = model.blocks[i]
+    C_, I = model.embed_dim, blk.mlp.fc1.weight.shape[0]
+    dev, p = dx.device, f"blocks.{i}."
+    d_t, d_s = descs
+    plain = ops.rowmap(C_)
+    delta = torch.empty(model.num_heads, rows, dtype=f32, device=dev)
+
+    def ln_bwd(dy, x_in, ln, name, mean, rstd, dres):
+        out = torch.empty(rows, C_, dtype=bf16, device=dev)
+        ops.layernorm_bwd(dy, plain, x_in, plain, ln.weight, mean, rstd, dres, plain, out, plain,
+                          grads[name + ".weight"], grads[name + ".bias"], rows, C_)
+        return out
+
+    def attn_bwd(pre_name, att, qkv, a, da, lse, h_in, desc):
+        dqkv = torch.empty(rows, 3 * C_, dtype=bf16, device=dev)
+        ops.seg_attention_bwd(qkv, a, da, lse, delta, dqkv, desc, 0.125)
+        return _linear_bwd(model, pre_name + "qkv", att.qkv, dqkv, h_in, grads)
+
+    # ---- out = x2 + fc2(gelu(fc1(LN(x2))))
+    dpre = _linear_bwd(model, p + "mlp.fc2", blk.mlp.fc2, dx, f1, grads, act=_lib.ACT_DGELU_ERF, aux=pre, ld_aux=I)
+    dln_m = _linear_bwd(model, p + "mlp.fc1", blk.mlp.fc1, dpre, ln_m, grads)
+    del dpre
+    dx2 = ln_bwd(dln_m, x2, blk.norm2, p + "norm2", mean_m, rstd_m, dx)
+    # ---- x2 = xt + proj(attn_s(LN(xt)))
+    da_s = _linear_bwd(model, p + "attn.proj", blk.attn.proj, dx2, a_s, grads)
+    dln_s = attn_bwd(p + "attn.", blk.attn, qkv_s, a_s, da_s, lse_s, ln_s, d_s)
+    dxt = ln_bwd(dln_s, xt, blk.norm1, p + "norm1", mean_s, rstd_s, dx2)
+    # ---- xt = x + temporal_fc(proj_t(attn_t(LN(x))))
+    dp_t = _linear_bwd(model, p + "temporal_fc", blk.temporal_fc, dxt, p_t, grads)
+    da_t = _linear_bwd(model, p + "temporal_attn.proj", blk.temporal_attn.proj, dp_t, a_t, grads)
+    dln_t = attn_bwd(p + "temporal_attn.", blk.temporal_attn, qkv_t, a_t, da_t, lse_t, ln_t, d_t)
+    return ln_bwd(dln_t, x, blk.temporal_norm1, p + "temporal_norm1", mean_t, rstd_t, dxt)
+
+
+class _TimeSformerFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: TimeSformer, names: List[str], x: torch.Tensor, *params):
+        B, T, C_, H, W = x.shape
+        if C_ != model.embed_dim:
+            raise ValueError(f"expected {model.embed_dim} channels, got {C_}")
+        HW, rows = H * W, B * H * W * T
+        save = any(ctx.needs_input_grad[2:])
+        x = x.contiguous()
+        pos_tab, time_tab = _tables(model, T, H, W)
+        tok = torch.empty(rows, C_, dtype=bf16, device=x.device)
+        ops.tsf_embed_fwd(x, pos_tab, time_tab, tok, B, T, C_, HW)
+        descs = (ops.temporal_desc(rows, T, model.num_heads, 3 * C_, C_),
+                 ops.spatial_desc(B, T, HW, model.num_heads, 3 * C_, C_))
+        saved = []
+        for i in range(model.depth):
+            tok, sv = _block_fwd(model, i, tok, descs, rows, save)
+            saved.append(sv)
+        out = torch.empty(B, T, C_, H, W, dtype=x.dtype, device=x.device)   # timesformer.py:523 (values; contiguous)
+        ops.tsf_untokenize(tok, out, B, T, C_, HW)
+        if save:
+            ctx.model, ctx.names, ctx.saved, ctx.descs = model, names, saved, descs
+            ctx.dims = (B, T, C_, H, W)
+            ctx.x_dtype = x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        model, names, saved, descs = ctx.model, ctx.names, ctx.saved, ctx.descs
+        B, T, C_, H, W = ctx.dims
+        HW, rows = H * W, B * H * W * T
+        dev = d_out.device
+        dtok = torch.empty(rows, C_, dtype=bf16, device=dev)
+        ops.tsf_embed_fwd(d_out.contiguous(), None, None, dtok, B, T, C_, HW)
+        grads: Dict[str, torch.Tensor] = {}
+        for i in reversed(range(model.depth)):
+            shapes = {n: tuple(p.shape) for n, p in model.blocks[i].named_parameters(prefix=f"blocks.{i}")}
+            _alloc_flat(shapes, grads, dev)
+            dtok = _block_bwd(model, i, dtok, saved[i], descs, grads, rows)
+            saved[i] = None
+        dx = None
+        if ctx.needs_input_grad[2]:
+            dx = torch.empty(B, T, C_, H, W, dtype=ctx.x_dtype, device=dev)
+            ops.tsf_untokenize(dtok, dx, B, T, C_, HW)
+        # table gradients: column sums of the token gradient over the broadcast dimensions
+        d_time_tab = torch.zeros(T * C_, dtype=f32, device=dev)
+        ops.colsum(dtok.view(B * HW, T * C_), d_time_tab)
+        d_pos_full = torch.zeros(HW * T * C_, dtype=f32, device=dev)
+        ops.colsum(dtok.view(B, HW * T * C_), d_pos_full)
+        d_pos_tab = d_pos_full.view(HW, T, C_).sum(1)
+        with torch.enable_grad():   # pull them back through the (tiny, linear) table interpolation
+            pp = model.pos_embed.detach().requires_grad_(True)
+            tp = model.time_embed.detach().requires_grad_(True)
+            pos_tab, time_tab = _tables(model, T, H, W, pp, tp)
+            grads["pos_embed"], grads["time_embed"] = torch.autograd.grad(
+                [pos_tab, time_tab], [pp, tp], [d_pos_tab, d_time_tab.view(T, C_)])
+        ctx.saved = None
+        return (None, None, dx) + tuple(grads[n] if ctx.needs_input_grad[3 + j] else None for j, n in enumerate(names))

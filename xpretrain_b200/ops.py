@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import XpGemm, XpRowMap, check, lib
+from ._lib import XpGemm, XpRowMap, XpSegAttn, check, lib
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -243,3 +243,44 @@ def nce_softmax_grad(z, logit_scale, lse_r, lse_c, g_scaled, loss, d_logit_scale
     N, ld = z.shape[0], z.stride(0)
     check(lib().xp_nce_softmax_grad(_p(z), _p(logit_scale), _p(lse_r), _p(lse_c), _p(g_scaled), _p(loss),
                                     _p(d_logit_scale), N, ld, _stream()), "xp_nce_softmax_grad")
+
+
+# ------------------------------------------------------------- config #4: TimeSformer (HD-VILA)
+def seg_desc(n_rows: int, heads: int, ld_qkv: int, ld_out: int, *, n_seq: int, seq_len: int, seg_len: int, inner: int,
+             outer_stride: int, inner_stride: int, tok_stride: int) -> XpSegAttn:
+    d = XpSegAttn()
+    d.n_rows, d.ld_qkv, d.ld_out = n_rows, ld_qkv, ld_out
+    d.outer_stride, d.inner_stride, d.tok_stride = outer_stride, inner_stride, tok_stride
+    d.heads, d.n_seq, d.seq_len, d.seg_len, d.inner, d.reserved = heads, n_seq, seq_len, seg_len, inner, 0
+    return d
+
+
+def temporal_desc(n_rows: int, T: int, heads: int, ld_qkv: int, ld_out: int) -> XpSegAttn:
+    """'(b h w) t m' groups of timesformer.py:210: T consecutive rows each; 64 // T groups share one CTA tile."""
+    G = max(1, 64 // T)
+    return seg_desc(n_rows, heads, ld_qkv, ld_out, n_seq=(n_rows + G * T - 1) // (G * T), seq_len=G * T, seg_len=T,
+                    inner=1, outer_stride=G * T, inner_stride=0, tok_stride=1)
+
+
+def spatial_desc(B: int, T: int, HW: int, heads: int, ld_qkv: int, ld_out: int) -> XpSegAttn:
+    """'(b t) (h w) m' groups of timesformer.py:217: H*W tokens, T rows apart."""
+    return seg_desc(B * HW * T, heads, ld_qkv, ld_out, n_seq=B * T, seq_len=HW, seg_len=HW, inner=T,
+                    outer_stride=HW * T, inner_stride=1, tok_stride=T)
+
+
+def seg_attention_fwd(qkv, out, lse, desc: XpSegAttn):
+    check(lib().xp_seg_attention_fwd(_p(qkv), _p(out), _p(lse), C.byref(desc), _stream()), "xp_seg_attention_fwd")
+
+
+def seg_attention_bwd(qkv, out, dout, lse, delta, dqkv, desc: XpSegAttn, q_scale: float):
+    check(lib().xp_seg_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), C.byref(desc), q_scale,
+                                     _stream()), "xp_seg_attention_bwd")
+
+
+def tsf_embed_fwd(x, pos, time, tokens, B, T, C_, HW):
+    check(lib().xp_tsf_embed_fwd(_p(x), _DT[x.dtype], _p(pos), _p(time), _p(tokens), B, T, C_, HW, _stream()),
+          "xp_tsf_embed_fwd")
+
+
+def tsf_untokenize(tokens, x, B, T, C_, HW):
+    check(lib().xp_tsf_untokenize(_p(tokens), _p(x), _DT[x.dtype], B, T, C_, HW, _stream()), "xp_tsf_untokenize")
