@@ -225,6 +225,30 @@ def run_ours(args):
                 "launches_per_step": len(rec), "gemm_ms_per_step": round(g_ms, 3),
                 "gemm_share_of_step": round(g_ms / ms_resident, 4)}
 
+    # ---- extra (not part of `value`): the fused clip + AdamW step on this model's gradients;
+    #      HBM-bound: 28 B per parameter (read p, g, m, v; write p, m, v) + 4 B for the norm pass
+    opt_info = None
+    if world == 1:
+        from xpretrain_b200.optimization.adamw import AdamW, build_e2e_optimizer_w_lr_mul
+        opt = AdamW(build_e2e_optimizer_w_lr_mul(list(model.named_parameters()), 0.0, 0.2), lr=0.0, betas=(0.9, 0.98))
+        step(*resident[0])                      # fresh gradients; lr = 0 keeps the weights (and later legs) unchanged
+        for _ in range(2):
+            opt.step(max_grad_norm=5.0)
+        torch.cuda.synchronize()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(5):
+            opt.step(max_grad_norm=5.0)
+        o1.record()
+        torch.cuda.synchronize()
+        n_par = sum(p.numel() for p in params)
+        o_ms = o0.elapsed_time(o1) / 5
+        hbm = measured_peaks().get("hbm_gbs", 6576.4)
+        opt_info = {"what": "global-norm clip + AdamW over all parameters, 3 kernel launches", "ms": round(o_ms, 3),
+                    "params": n_par, "gbs": round(32.0 * n_par / o_ms / 1e6, 1), "hbm_peak_gbs": hbm,
+                    "frac_of_hbm_peak": round(32.0 * n_par / o_ms / 1e6 / hbm, 3)}
+        del opt
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -250,6 +274,7 @@ def run_ours(args):
         "gpu_launches": int(launches * world),
         "clocks": clocks,
         "roofline": roof,
+        "optimizer_step": opt_info,
         "whole_step": {"flops_per_pair": fm["train"], "tflops_per_gpu": round(value / world * fm["train"] / 1e12, 1),
                        "frac_of_peak": round(value / world * fm["train"] / 1e12 / peaks["tflops"], 4)},
     }

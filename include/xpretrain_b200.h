@@ -214,6 +214,38 @@ int xp_tsf_embed_fwd(const void* x, int32_t x_dtype, const float* pos, const flo
 int xp_tsf_untokenize(const void* tokens_bf16, void* x, int32_t x_dtype, int32_t B, int32_t T, int32_t C, int32_t HW,
                       void* stream);
 
+/* ---- the optimizer step.  Replaces AdamW.step (CLIP-ViP/src/optimization/adamw.py:40-103) and
+ * torch.nn.utils.clip_grad_norm_ as called at pretrain/run_pretrain.py:408-411,422 — one table-driven launch over all
+ * parameters instead of ~10 elementwise launches per parameter.
+ *
+ * table_dev:     device array of XpOptTensor, one per parameter (all fp32, contiguous).  step_size =
+ *                lr * sqrt(1 - beta2^t) / (1 - beta1^t) (or lr when correct_bias is off) and decay = lr * weight_decay are
+ *                computed by the host per parameter group; p_bf16 (optional) receives the bf16 copy of the updated p.
+ * block_map_dev: device array of n_blocks {tensor index, chunk index} int32 pairs; chunk c of a tensor covers elements
+ *                [c * xp_opt_chunk_elems(), ...).  Built once per parameter set by the host.
+ * xp_opt_grad_norm:  norm_out_dev[0] = 2-norm over every g in the table, norm_out_dev[1] = min(1, max_norm/(norm+1e-6))
+ *                    (1 if max_norm <= 0); partial_dev is n_blocks floats of scratch.  Deterministic.
+ * xp_opt_scale_grads: g *= norm_dev[1] in place (clip_grad_norm_ used on its own).
+ * xp_opt_adamw_step:  the fused update; norm_dev (optional) = the pair above, its coefficient is applied to g on the fly. */
+typedef struct XpOptTensor {
+  void* p;
+  const void* g;
+  void* m;
+  void* v;
+  void* p_bf16;
+  int64_t n;
+  float step_size;
+  float decay;
+  int32_t reserved[2];
+} XpOptTensor;
+int32_t xp_opt_chunk_elems(void);
+int xp_opt_grad_norm(const XpOptTensor* table_dev, const int32_t* block_map_dev, int32_t n_blocks, float* partial_dev,
+                     float max_norm, float* norm_out_dev, void* stream);
+int xp_opt_scale_grads(const XpOptTensor* table_dev, const int32_t* block_map_dev, int32_t n_blocks, const float* norm_dev,
+                       void* stream);
+int xp_opt_adamw_step(const XpOptTensor* table_dev, const int32_t* block_map_dev, int32_t n_blocks, const float* norm_dev,
+                      float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,3 +137,35 @@ def test_timesformer_flop_model_matches_baseline_md():
     assert abs(TO.flops_per_sample(cfg, 7, 10, 16) / 1e9 - 162.78) < 0.01
     assert abs(TO.flops_per_sample(cfg, 8, 7, 7) / 1e9 - 56.27) < 0.01
     assert abs(TO.flops_per_sample(cfg, 8, 28, 28) / 1e9 - 975.81) < 0.01
+
+
+# ------------------------------------------------------------------ optimizer step
+def test_adamw_oracle_replays_reference_trajectory(golden_dir):
+    from oracle import adamw_oracle as AO
+
+    gold = torch.load(os.path.join(golden_dir, "adamw_8steps.pt"), weights_only=False)
+    cfg, shapes = gold["cfg"], gold["shapes"]
+    g0 = torch.Generator().manual_seed(0)
+    p = {n: torch.randn(s, generator=g0) for n, s in shapes.items()}
+    m = {n: torch.zeros_like(v) for n, v in p.items()}
+    v = {n: torch.zeros_like(x) for n, x in p.items()}
+    named = [(n, torch.nn.Parameter(p[n].clone())) for n in shapes]
+    groups = AO.param_groups(named, cfg["learning_rate"], cfg["weight_decay"], cfg["lr_mul"], cfg["lr_mul_prefix"])
+    name_of = {id(q): n for n, q in named}
+    assert [[name_of[id(q)] for q in g["params"]] for g in groups] == gold["group_names"]
+    for step in range(1, cfg["steps"] + 1):
+        lr = AO.lr_schedule(step, cfg["decay"], cfg["learning_rate"], cfg["num_train_steps"], cfg["warmup_ratio"])
+        assert lr == gold["lrs"][step - 1]
+        scale = 0.01 if step % 3 == 0 else 1.0
+        grads = {n: torch.randn(s, generator=torch.Generator().manual_seed(1000 * step + i)) * scale
+                 for i, (n, s) in enumerate(shapes.items())}
+        total, coef = AO.clip_coef([grads[n] for n in shapes], cfg["grad_norm"])
+        assert abs(float(total) - gold["norms"][step - 1]) < 1e-5 * gold["norms"][step - 1]
+        for gi, g in enumerate(groups):
+            for q in g["params"]:
+                n = name_of[id(q)]
+                AO.adamw_step(p[n], grads[n] * coef, m[n], v[n], step, cfg["lr_mul"] * lr if gi < 2 else lr,
+                              tuple(cfg["betas"]), 1e-6, g["weight_decay"], True)
+    for n in shapes:
+        assert torch.equal(p[n], gold["final_p"][n]) and torch.equal(m[n], gold["final_m"][n]), n
+        assert torch.equal(v[n], gold["final_v"][n]), n
