@@ -225,6 +225,28 @@ def run_ours(args):
                 "launches_per_step": len(rec), "gemm_ms_per_step": round(g_ms, 3),
                 "gemm_share_of_step": round(g_ms / ms_resident, 4)}
 
+    # ---- BASELINE.json metric (2): ViT-block %-of-tensor-roofline — CUDA events around each of the 12 ViP blocks
+    #      (QKV + proxy-token attention + out-proj + MLP, K3-K8) of one un-instrumented step, fwd and fwd+bwd
+    vit_block = None
+    if rank == 0 or world > 1:
+        blk = []
+        model.clipmodel.block_timer = blk
+        step(*resident[0])
+        torch.cuda.synchronize()
+        model.clipmodel.block_timer = None
+        f_ms = [a.elapsed_time(b) for (k, a, b) in blk if k == "fwd"]
+        b_ms = [a.elapsed_time(b) for (k, a, b) in blk if k == "bwd"]
+        if f_ms and b_ms:
+            blk_flops = 34.825e9 * B                                  # one ViP block fwd, per sample
+            f_avg, b_avg = sum(f_ms) / len(f_ms), sum(b_ms) / len(b_ms)
+            pk = measured_peaks()["tflops"]
+            vit_block = {"what": f"one fused ViP encoder block (K3-K8), batch {B}, 2356 tokens, mean of {len(f_ms)} blocks",
+                         "fwd_ms": round(f_avg, 3), "fwd_tflops": round(blk_flops / f_avg / 1e9, 1),
+                         "fwd_frac_of_peak": round(blk_flops / f_avg / 1e9 / pk, 4),
+                         "fwd_bwd_ms": round(f_avg + b_avg, 3),
+                         "fwd_bwd_tflops": round(3 * blk_flops / (f_avg + b_avg) / 1e9, 1),
+                         "fwd_bwd_frac_of_peak": round(3 * blk_flops / (f_avg + b_avg) / 1e9 / pk, 4), "peak_tflops": pk}
+
     # ---- extra (not part of `value`): the fused clip + AdamW step on this model's gradients;
     #      HBM-bound: 28 B per parameter (read p, g, m, v; write p, m, v) + 4 B for the norm pass
     opt_info = None
@@ -274,6 +296,7 @@ def run_ours(args):
         "gpu_launches": int(launches * world),
         "clocks": clocks,
         "roofline": roof,
+        "vit_block": vit_block,
         "optimizer_step": opt_info,
         "whole_step": {"flops_per_pair": fm["train"], "tflops_per_gpu": round(value / world * fm["train"] / 1e12, 1),
                        "frac_of_peak": round(value / world * fm["train"] / 1e12 / peaks["tflops"], 4)},

@@ -213,6 +213,11 @@ int xp_tsf_embed_fwd(const void* x, int32_t x_dtype, const float* pos, const flo
                      int32_t T, int32_t C, int32_t HW, void* stream);
 int xp_tsf_untokenize(const void* tokens_bf16, void* x, int32_t x_dtype, int32_t B, int32_t T, int32_t C, int32_t HW,
                       void* stream);
+/* Stochastic depth on a residual branch (DropPath, timesformer.py:98-121, as Block.forward applies it :212,:218,:225):
+ * out[r,:] = (residual ? residual[r,:] : 0) + scale[r] * x[r,:], all [rows, C] bf16 contiguous, scale fp32 per row
+ * (0 or 1/keep_prob of the row's sample/group).  out may alias x. */
+int xp_rowscale_bf16(const void* x, const float* scale, const void* residual, void* out, int64_t rows, int32_t C,
+                     void* stream);
 
 /* ---- the optimizer step.  Replaces AdamW.step (CLIP-ViP/src/optimization/adamw.py:40-103) and
  * torch.nn.utils.clip_grad_norm_ as called at pretrain/run_pretrain.py:408-411,422 — one table-driven launch over all

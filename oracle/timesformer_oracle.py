@@ -111,8 +111,31 @@ def attention(x, w_qkv, b_qkv, w_proj, b_proj, heads: int):
     return F.linear(out, w_proj, b_proj)
 
 
-def block_forward(sd, i: int, x, B: int, T: int, H: int, W: int, cfg: TimeSformerCfg):
-    """timesformer.py:207-226 (divided_space_time).  x: [B, H*W*T, C], token order (h w t)."""
+def draw_drop_masks(cfg: TimeSformerCfg, B: int, T: int, H: int, W: int, drop_path_rate: float, device=None,
+                    dtype=torch.float32):
+    """Training-mode DropPath factors (timesformer.py:98-113) for every block, drawn from torch's global generator in the
+    reference's own order and shapes — block i with rate linspace(0, drop_path_rate, depth)[i] (:445) calls drop_path on
+    the temporal residual [(b h w), t, m] (:212), the spatial one [(b t), (h w), m] (:218) and the MLP one [b, n, m] (:225):
+    factor = floor(keep + U[0,1)) / keep per leading index.  Seeding torch identically therefore reproduces the reference's
+    masks exactly.  Returns a list of (m_t [B*H*W], m_s [B*T], m_m [B]) or None for blocks with rate 0."""
+    rates = [r.item() for r in torch.linspace(0, drop_path_rate, cfg.depth)]
+    out = []
+    for r in rates:
+        if r == 0.0:
+            out.append(None)
+            continue
+        keep = 1 - r
+        ms = []
+        for n in (B * H * W, B * T, B):
+            rnd = keep + torch.rand((n, 1, 1), dtype=dtype, device=device)
+            ms.append((rnd.floor_() / keep).reshape(n))
+        out.append(tuple(ms))
+    return out
+
+
+def block_forward(sd, i: int, x, B: int, T: int, H: int, W: int, cfg: TimeSformerCfg, drop=None):
+    """timesformer.py:207-226 (divided_space_time).  x: [B, H*W*T, C], token order (h w t).  `drop` = (m_t, m_s, m_m)
+    DropPath factors of this block (see draw_drop_masks) or None (eval mode / rate 0)."""
     p = f"blocks.{i}."
     C, HW = cfg.embed_dim, H * W
     ln = lambda t, n: F.layer_norm(t, (C,), sd[p + n + ".weight"], sd[p + n + ".bias"], cfg.eps)  # noqa: E731
@@ -120,18 +143,25 @@ def block_forward(sd, i: int, x, B: int, T: int, H: int, W: int, cfg: TimeSforme
     xt = x.reshape(B * HW, T, C)
     rt = attention(ln(xt, "temporal_norm1"), sd[p + "temporal_attn.qkv.weight"], sd[p + "temporal_attn.qkv.bias"],
                    sd[p + "temporal_attn.proj.weight"], sd[p + "temporal_attn.proj.bias"], cfg.num_heads)
+    if drop is not None:
+        rt = rt * drop[0][:, None, None]
     rt = F.linear(rt.reshape(B, HW * T, C), sd[p + "temporal_fc.weight"], sd[p + "temporal_fc.bias"])
     xt = x + rt
     # spatial: groups (b t), H*W tokens each
     xs = xt.reshape(B, HW, T, C).permute(0, 2, 1, 3).reshape(B * T, HW, C)
     rs = attention(ln(xs, "norm1"), sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"], sd[p + "attn.proj.weight"],
                    sd[p + "attn.proj.bias"], cfg.num_heads)
+    if drop is not None:
+        rs = rs * drop[1][:, None, None]
     rs = rs.reshape(B, T, HW, C).permute(0, 2, 1, 3).reshape(B, HW * T, C)
     x = xt + rs
     # MLP
     h = F.linear(ln(x, "norm2"), sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
     h = F.gelu(h)
-    return x + F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    h = F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    if drop is not None:
+        h = h * drop[2][:, None, None]
+    return x + h
 
 
 def embed(sd, x, cfg: TimeSformerCfg):
@@ -143,13 +173,14 @@ def embed(sd, x, cfg: TimeSformerCfg):
     return tok.reshape(B, H * W * T, C)
 
 
-def timesformer_forward(sd, x, cfg: TimeSformerCfg, return_hidden: bool = False):
-    """timesformer.py:481-525.  Returns [B, T, C, H, W] (the reference's permuted view)."""
+def timesformer_forward(sd, x, cfg: TimeSformerCfg, return_hidden: bool = False, drop_masks=None):
+    """timesformer.py:481-525.  Returns [B, T, C, H, W] (the reference's permuted view).  drop_masks: per-block DropPath
+    factors from draw_drop_masks (training mode) or None (eval)."""
     B, T, C, H, W = x.shape
     tok = embed(sd, x, cfg)
     hidden = [tok]
     for i in range(cfg.depth):
-        tok = block_forward(sd, i, tok, B, T, H, W, cfg)
+        tok = block_forward(sd, i, tok, B, T, H, W, cfg, None if drop_masks is None else drop_masks[i])
         hidden.append(tok)
     out = tok.reshape(B, H, W, T, C).permute(0, 3, 4, 1, 2)
     return (out, hidden) if return_hidden else out

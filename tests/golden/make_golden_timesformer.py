@@ -88,8 +88,52 @@ def run_case(ref, name, cfg, B, T, H, W, weight_seed, data_seed):
     torch.save(gold, os.path.join(HERE, f"{name}.pt"))
 
 
+def run_train_case(ref, name, cfg, B, T, H, W, weight_seed, data_seed, rate, torch_seed):
+    """Training mode: stochastic depth active (timesformer.py:98-121).  The oracle draws the DropPath factors from torch's
+    global generator in the reference's order, so seeding both identically must give the same forward and gradients."""
+    sd = O.init_state_dict(cfg, seed=weight_seed)
+    model = ref.TimeSformer(depth=cfg.depth, num_frames=cfg.num_frames, H=cfg.H, W=cfg.W, embed_dim=cfg.embed_dim,
+                            num_heads=cfg.num_heads, drop_path_rate=rate)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    x = O.synthetic_input(B, T, H, W, cfg, seed=data_seed).requires_grad_(True)
+    g = torch.Generator().manual_seed(data_seed + 1)
+    w_out = torch.randn(B, T, cfg.embed_dim, H, W, generator=g) / (B * T * H * W) ** 0.5
+    torch.manual_seed(torch_seed)
+    out = model(x)
+    loss = (out * w_out).sum()
+    loss.backward()
+    ref_grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    torch.manual_seed(torch_seed)
+    masks = O.draw_drop_masks(cfg, B, T, H, W, rate)
+    dropped = sum(int((m == 0).sum()) for blk in masks if blk is not None for m in blk)
+    assert masks[0] is None and dropped > 0, "the case must actually drop some paths"
+    sdo = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = x.detach().clone().requires_grad_(True)
+    out_o = O.timesformer_forward(sdo, xo, cfg, drop_masks=masks)
+    (out_o * w_out).sum().backward()
+    e_out, e_dx = rel(out_o, out), rel(xo.grad, x.grad)
+    worst = max(float((sdo[n].grad - gr).norm()) / max(float(gr.norm()), 1e-3 * float(ref_grads["blocks.0.mlp.fc1.weight"].norm()))
+                for n, gr in ref_grads.items())
+    print(f"{name}: {dropped} dropped paths; out {e_out:.2e} dx {e_dx:.2e} worst param grad {worst:.2e}")
+    assert e_out < 2e-6 and e_dx < 2e-5 and worst < 5e-5
+    keep = ("blocks.1.temporal_fc.weight", "blocks.1.temporal_attn.proj.weight", "blocks.1.attn.proj.weight",
+            "blocks.1.attn.proj.bias", "blocks.1.mlp.fc2.weight", "blocks.1.mlp.fc2.bias", "blocks.2.mlp.fc1.weight",
+            "blocks.0.attn.qkv.weight", "time_embed")
+    torch.save({"cfg": vars(cfg), "B": B, "T": T, "H": H, "W": W, "weight_seed": weight_seed, "data_seed": data_seed,
+                "rate": rate, "torch_seed": torch_seed, "masks": masks, "out": out.detach().clone(), "loss": loss.detach(),
+                "dx_t0": x.grad[:, 0].detach().clone(),
+                "grads": {n: (ref_grads[n][:8].clone() if ref_grads[n].dim() == 2 else ref_grads[n].clone()) for n in keep},
+                "grad_norms": {n: float(ref_grads[n].norm()) for n in keep}},
+               os.path.join(HERE, f"{name}.pt"))
+
+
 def main():
     ref = load_reference()
+    # training mode with DropPath: 3 blocks (rates 0, 0.25, 0.5), B = 4 so that sample-level drops occur
+    run_train_case(ref, "timesformer_train_droppath", O.TimeSformerCfg(depth=3, num_frames=4, H=3, W=4, embed_dim=128, num_heads=2),
+                   B=4, T=4, H=3, W=4, weight_seed=2, data_seed=13, rate=0.5, torch_seed=77)
     # head_dim 64 (the kernels' head size); both interpolation paths: grid 4x6 -> 3x5, frames 4 -> 3
     run_case(ref, "timesformer_interp_b2", O.TimeSformerCfg(depth=2, num_frames=4, H=4, W=6, embed_dim=128, num_heads=2),
              B=2, T=3, H=3, W=5, weight_seed=0, data_seed=11)

@@ -96,15 +96,16 @@ def test_no_cpu_path():
         AdamW([p]).step()
 
 
-def test_one_training_step_of_vidclip_lowers_the_loss(dev):
-    """fwd + InfoNCE + bwd + clip + AdamW on the dual encoder (tiny depth): the loss on the same batch must drop."""
+def test_training_step_on_the_dual_encoder_matches_the_oracle_update(dev):
+    """fwd + InfoNCE + bwd + fused clip + AdamW on VidCLIP (depth 1): every parameter moves exactly as adamw.py says for
+    the gradients the backward produced, and the next forward really uses the updated weights (bf16 copies refreshed)."""
+    from types import SimpleNamespace
+
     from oracle import clipvip_oracle as O
     from xpretrain_b200.modeling.clip_vip import ClipVipConfig, TowerConfig
     from xpretrain_b200.modeling.vidclip import VidCLIP
     from xpretrain_b200.optimization import build_loss_func
     from xpretrain_b200.optimization.adamw import AdamW, build_e2e_optimizer_w_lr_mul
-
-    from types import SimpleNamespace
 
     ocfg = O.ClipVipCfg(vision=O.TowerCfg(768, 12, 1, 3072), text=O.TowerCfg(512, 8, 1, 2048))
     add = SimpleNamespace(type="ViP", temporal_size=ocfg.temporal_size, if_use_temporal_embed=1,
@@ -114,13 +115,26 @@ def test_one_training_step_of_vidclip_lowers_the_loss(dev):
     video, ids, mask = O.synthetic_batch(8, 2, 16, ocfg, seed=3)
     video, ids, mask = video.to(dev), ids.to(dev), mask.to(dev)
     loss_fn = build_loss_func({"loss_name": "NCELearnableTempLoss"})
-    opt = AdamW(build_e2e_optimizer_w_lr_mul(list(model.named_parameters()), 1e-4, 0.2), lr=1e-4, betas=(0.9, 0.98))
-    losses = []
-    for _ in range(3):
+    lr, wd, betas = 1e-4, 0.2, (0.9, 0.98)
+    named = list(model.named_parameters())
+    opt = AdamW(build_e2e_optimizer_w_lr_mul(named, lr, wd), lr=lr, betas=betas)
+
+    def loss_of():
         out = model(video=video, text_input_ids=ids, text_input_mask=mask)
-        loss = loss_fn(out["vis_features"], out["text_features"], model.clipmodel.logit_scale)
-        losses.append(float(loss))
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step(max_grad_norm=5.0)
-    assert losses[2] < losses[0], losses
+        return loss_fn(out["vis_features"], out["text_features"], model.clipmodel.logit_scale)
+
+    loss0 = loss_of()
+    loss0.backward()
+    before = {n: (p.detach().cpu().clone(), p.grad.detach().cpu().clone()) for n, p in named}
+    total, coef = AO.clip_coef([g for _, g in before.values()], 5.0)
+    opt.step(max_grad_norm=5.0)
+    assert abs(float(opt.last_grad_norm) - float(total)) < 1e-4 * float(total)
+    for n, p in named:
+        rp, g = before[n]
+        m, v = torch.zeros_like(rp), torch.zeros_like(rp)
+        decayed = not any(k in n for k in AO.NO_DECAY)
+        AO.adamw_step(rp, g * coef, m, v, 1, lr, betas, 1e-6, wd if decayed else 0.0, True)
+        assert torch.allclose(p.detach().cpu(), rp, rtol=1e-5, atol=1e-7), n
+    with torch.no_grad():
+        loss1 = loss_of()
+    assert float(loss1) != float(loss0)        # the bf16 compute copies were refreshed from the updated masters

@@ -177,8 +177,49 @@ def test_full_width_block_against_fp32_oracle_on_gpu(dev):
         assert c > 0.99, (n, c)
 
 
-def test_training_mode_with_drop_path_is_refused_not_silently_changed(dev):
-    cfg = TO.TimeSformerCfg(depth=1, embed_dim=128, num_heads=2, H=2, W=2, num_frames=2)
-    model = _build(cfg, TO.init_state_dict(cfg, seed=0), dev).train()
-    with pytest.raises(NotImplementedError):
-        model(torch.randn(1, 2, 128, 2, 2, device=dev))
+def test_training_mode_drop_path_matches_reference_golden(dev, golden_dir):
+    """Training mode with stochastic depth: the reference's own train() forward/backward (seeded) vs ours with the same
+    dropped paths (the golden stores the factors the reference drew)."""
+    gold = torch.load(os.path.join(golden_dir, "timesformer_train_droppath.pt"), weights_only=False)
+    cfg = TO.TimeSformerCfg(**gold["cfg"])
+    from xpretrain_b200.modeling.timesformer import TimeSformer
+
+    model = TimeSformer(depth=cfg.depth, num_frames=cfg.num_frames, H=cfg.H, W=cfg.W, embed_dim=cfg.embed_dim,
+                        num_heads=cfg.num_heads, drop_path_rate=gold["rate"])
+    model.load_state_dict(TO.init_state_dict(cfg, seed=gold["weight_seed"]), strict=True)
+    model = model.to(dev).train()
+    model.forced_drop_masks = [None if m is None else tuple(t.to(dev) for t in m) for m in gold["masks"]]
+    B, T, H, W = gold["B"], gold["T"], gold["H"], gold["W"]
+    x = TO.synthetic_input(B, T, H, W, cfg, seed=gold["data_seed"]).to(dev).requires_grad_(True)
+    g = torch.Generator().manual_seed(gold["data_seed"] + 1)
+    w_out = (torch.randn(gold["out"].shape, generator=g) / (B * T * H * W) ** 0.5).to(dev)
+    out = model(x)
+    (out * w_out).sum().backward()
+    assert _rel(out.detach().cpu(), gold["out"]) < 1.5e-2
+    assert _cos(x.grad[:, 0].cpu(), gold["dx_t0"]) > 0.995
+    grads = dict(model.named_parameters())
+    for n, ref in gold["grads"].items():
+        got = grads[n].grad
+        got = (got[:8] if ref.dim() == 2 else got).cpu()
+        assert _cos(got, ref) > 0.99, (n, _cos(got, ref))
+    # the same masks in eval mode are ignored (no path is dropped): the output must differ from the training one
+    with torch.no_grad():
+        out_eval = model.eval()(x)
+    assert _rel(out_eval, out.detach()) > 1e-2
+
+
+def test_training_mode_draws_the_references_rng_stream(dev):
+    """Fresh draws: same torch.rand calls / shapes / order as drop_path (timesformer.py:98-113), so seeding torch the same
+    way on the same device gives the factors the oracle's restatement draws."""
+    from xpretrain_b200.modeling.timesformer import TimeSformer
+
+    cfg = TO.TimeSformerCfg(depth=3, num_frames=4, H=3, W=4, embed_dim=128, num_heads=2)
+    model = TimeSformer(depth=3, num_frames=4, H=3, W=4, embed_dim=128, num_heads=2, drop_path_rate=0.5).to(dev)
+    torch.manual_seed(5)
+    ours = model.draw_drop_masks(4, 4, 3, 4, dev, torch.float32)
+    torch.manual_seed(5)
+    want = TO.draw_drop_masks(cfg, 4, 4, 3, 4, 0.5, device=dev)
+    assert ours[0] is None and want[0] is None
+    for a, b in zip(ours[1:], want[1:]):
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)

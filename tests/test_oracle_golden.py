@@ -169,3 +169,30 @@ def test_adamw_oracle_replays_reference_trajectory(golden_dir):
     for n in shapes:
         assert torch.equal(p[n], gold["final_p"][n]) and torch.equal(m[n], gold["final_m"][n]), n
         assert torch.equal(v[n], gold["final_v"][n]), n
+
+
+def test_timesformer_oracle_training_mode_drop_path_golden(golden_dir):
+    """Training mode (stochastic depth): the oracle with the factors the reference drew reproduces the reference's
+    train() forward and gradients; and re-drawing them under the stored torch seed gives the same factors."""
+    from oracle import timesformer_oracle as TO
+
+    gold = torch.load(os.path.join(golden_dir, "timesformer_train_droppath.pt"), weights_only=False)
+    cfg = TO.TimeSformerCfg(**gold["cfg"])
+    B, T, H, W = gold["B"], gold["T"], gold["H"], gold["W"]
+    torch.manual_seed(gold["torch_seed"])
+    redraw = TO.draw_drop_masks(cfg, B, T, H, W, gold["rate"])
+    for a, b in zip(redraw, gold["masks"]):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert all(torch.equal(u, v) for u, v in zip(a, b))
+    sd = {k: v.clone().requires_grad_(True) for k, v in TO.init_state_dict(cfg, seed=gold["weight_seed"]).items()}
+    x = TO.synthetic_input(B, T, H, W, cfg, seed=gold["data_seed"]).requires_grad_(True)
+    g = torch.Generator().manual_seed(gold["data_seed"] + 1)
+    w_out = torch.randn(gold["out"].shape, generator=g) / (B * T * H * W) ** 0.5
+    out = TO.timesformer_forward(sd, x, cfg, drop_masks=gold["masks"])
+    assert _rel(out.detach(), gold["out"]) < 1e-5
+    (out * w_out).sum().backward()
+    assert _rel(x.grad[:, 0], gold["dx_t0"]) < 1e-4
+    for n, ref in gold["grads"].items():
+        got = sd[n].grad[:8] if ref.dim() == 2 else sd[n].grad
+        assert float((got - ref).norm()) < 1e-4 * gold["grad_norms"][n] + 1e-9, n

@@ -282,9 +282,48 @@ cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ 
   }
 }
 
+// ------------------------------------------------- per-row scale (+ residual): stochastic depth
+// out[r, :] = (res ? res[r, :] : 0) + scale[r] * x[r, :]   — DropPath of timesformer.py:98-113 applied to a residual
+// branch: scale[r] is 0 or 1/keep_prob for the sample (or group) row r belongs to.  One thread per 8 columns.
+__global__ void __launch_bounds__(256)
+rowscale_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const __nv_bfloat16* __restrict__ res,
+                __nv_bfloat16* __restrict__ out, long long rows, int C) {
+  const int vec = C >> 3;
+  const long long idx = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (idx >= rows * vec) return;
+  const long long r = idx / vec;
+  const long long off = r * C + (idx - r * vec) * 8;
+  const float s = scale[r];
+  float v[8];
+  unpack8(*reinterpret_cast<const uint4*>(x + off), v);
+  if (res != nullptr) {
+    float q[8];
+    unpack8(*reinterpret_cast<const uint4*>(res + off), q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = q[j] + s * v[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= s;
+  }
+  *reinterpret_cast<uint4*>(out + off) = pack8(v);
+}
+
 }  // namespace xp
 
 using namespace xp;
+
+extern "C" int xp_rowscale_bf16(const void* x, const float* scale, const void* residual, void* out, int64_t rows, int32_t C,
+                                void* stream) {
+  XP_ENTER(x);
+  if (C % 8) return fail("xp_rowscale_bf16: C must be a multiple of 8");
+  if (rows <= 0) return 0;
+  const long long n = rows * (C / 8);
+  rowscale_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), scale, static_cast<const __nv_bfloat16*>(residual),
+      static_cast<__nv_bfloat16*>(out), rows, C);
+  XP_CHECK_LAUNCH("rowscale_kernel");
+  return 0;
+}
 
 extern "C" int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMap* ymap,
                                 const float* gamma, const float* beta, float* mean, float* rstd, int64_t rows,

@@ -414,8 +414,15 @@ def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
         return lse
 
     layer_saved = []
+    timer = getattr(model, "block_timer", None)   # bench.py: CUDA events around each ViP block (metric 2 of BASELINE.json)
     for i, layer in enumerate(vm.encoder.layers):
+        if timer is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         x, sv = _layer_fwd(x, layer, pk, i, eps, attn_fwd, rows, save)
+        if timer is not None:
+            e1.record()
+            timer.append(("fwd", e0, e1))
         layer_saved.append(sv)
     # pooled = post_layernorm(last_hidden[:, 0])  (CLIP_ViP.py:891-893): CLS rows picked by the row map
     cls_map = ops.rowmap(C_, group=1, group_stride=S * C_)
@@ -454,9 +461,16 @@ def _vision_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str,
     def attn_bwd(qkv, a, da, lse, dqkv):
         ops.vip_attention_bwd(qkv, a, da, lse, dqkv, sv.ws, B, H, T, L, M, C_, 0.125)
 
+    timer = getattr(model, "block_timer", None)
     for i in reversed(range(len(vm.encoder.layers))):
         prefix = f"vision_model.encoder.layers.{i}."
+        if timer is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         dx = _layer_bwd(dx, sv.layers[i], vm.encoder.layers[i], pk, i, grads, prefix, attn_bwd, rows)
+        if timer is not None:
+            e1.record()
+            timer.append(("bwd", e0, e1))
         sv.layers[i] = None
         _grads_ready(model, grads, prefix)
     # pre_layrnorm backward, written as two compact halves: patch rows [B, T*L, C] and global rows [B, M, C]

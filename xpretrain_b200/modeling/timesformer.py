@@ -11,8 +11,11 @@ The module tree only holds parameters.  forward/backward run as ONE autograd.Fun
   * both attentions are `xp_seg_attention_*` reading the fused qkv buffer through strides — the six einops rearranges
     per block of timesformer.py:210-219 never materialise,
   * LayerNorm fwd/bwd are the row kernels shared with CLIP-ViP.
-There is no CPU path.  Stochastic depth (DropPath, timesformer.py:98-121) is NOT implemented yet: training-mode
-forward with drop_path_rate > 0 raises instead of silently changing the regulariser (eval mode is exact).
+  * stochastic depth (DropPath, timesformer.py:98-121) in training mode: the per-group keep factors are drawn with the
+    reference's own torch.rand calls (same shapes and order, so the same seed drops the same paths) and applied by a
+    row-scale kernel on the three residual branches (one extra elementwise pass each; eval mode fuses the residual add
+    into the GEMM epilogue).
+There is no CPU path.
 """
 from __future__ import annotations
 
@@ -79,6 +82,7 @@ class TimeSformer(nn.Module):
         self.blocks = nn.ModuleList([_TsfBlock(embed_dim, hidden, qkv_bias, self.eps) for _ in range(depth)])
         self.norm = nn.LayerNorm(embed_dim, eps=self.eps)   # constructed, never applied (timesformer.py:451)
         self._cache: Dict[str, list] = {}
+        self.forced_drop_masks = None     # tests: per-block (m_t, m_s, m_m) factors instead of fresh random draws
         self._init_weights()
 
     def _init_weights(self):
@@ -101,14 +105,31 @@ class TimeSformer(nn.Module):
     def no_weight_decay(self):
         return {'pos_embed', 'time_embed'}
 
+    def draw_drop_masks(self, B: int, T: int, H: int, W: int, device, dtype):
+        """Stochastic-depth factors of one training forward (timesformer.py:98-113): block i (rate
+        linspace(0, drop_path_rate, depth)[i], :445) draws, in this order, floor(keep + U[0,1)) / keep per temporal group
+        (b h w) (:212), per spatial group (b t) (:218) and per sample (:225) — the same torch.rand calls, shapes and
+        order as the reference, so an identically seeded run drops the same paths."""
+        masks = []
+        for r in [v.item() for v in torch.linspace(0, self.drop_path_rate, self.depth)]:
+            if r == 0.0:
+                masks.append(None)
+                continue
+            keep = 1 - r
+            masks.append(tuple(((keep + torch.rand((n, 1, 1), dtype=dtype, device=device)).floor_() / keep).reshape(n).float()
+                               for n in (B * H * W, B * T, B)))
+        return masks
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise _lib.XpError("xpretrain_b200 TimeSformer needs CUDA tensors on a B200: there is no CPU path")
-        if self.training and self.drop_path_rate > 0 and torch.is_grad_enabled():
-            raise NotImplementedError("stochastic depth (DropPath) is not implemented: build with drop_path_rate=0 "
-                                      "or call .eval()")
+        masks = None
+        if self.training and self.drop_path_rate > 0:
+            B, T, _, H, W = x.shape
+            masks = self.forced_drop_masks if self.forced_drop_masks is not None else \
+                self.draw_drop_masks(B, T, H, W, x.device, x.dtype)
         names, params = zip(*[(n, p) for n, p in self.named_parameters() if not n.startswith("norm.")])
-        return _TimeSformerFunction.apply(self, list(names), x, *params)
+        return _TimeSformerFunction.apply(self, list(names), masks, x, *params)
 
 
 # ----------------------------------------------------------------------------------- helpers
@@ -159,35 +180,58 @@ def _attn_fwd(model, pre: str, att: _TsfAttention, h, desc, rows: int, C_: int):
     return qkv, a, lse
 
 
-def _block_fwd(model: TimeSformer, i: int, x, descs, rows: int, save: bool):
-    """timesformer.py:207-226.  x: [rows, C] bf16 tokens, (h w t) order."""
+def _row_scales(masks, B: int, T: int, HW: int):
+    """Per-token-row DropPath factors (rows ordered (b, p, t)) from the per-group factors of one block."""
+    if masks is None:
+        return None
+    m_t, m_s, m_m = masks
+    return (m_t.repeat_interleave(T).contiguous(),
+            m_s.view(B, 1, T).expand(B, HW, T).reshape(-1).contiguous(),
+            m_m.repeat_interleave(HW * T).contiguous())
+
+
+def _residual_linear(model, name: str, lin: nn.Linear, a, residual, scale, rows: int, C_: int):
+    """residual + drop_path(lin(a)): fused into the GEMM epilogue when no path is dropped, else GEMM + one row-scale pass."""
+    out = torch.empty(rows, C_, dtype=bf16, device=a.device)
+    if scale is None:
+        ops.linear_fwd(a, _w(model, name + ".weight", lin.weight), lin.bias, out, residual=residual, ldr=C_)
+    else:
+        tmp = torch.empty(rows, C_, dtype=bf16, device=a.device)
+        ops.linear_fwd(a, _w(model, name + ".weight", lin.weight), lin.bias, tmp)
+        ops.rowscale(tmp, scale, out, residual=residual)
+    return out
+
+
+def _block_fwd(model: TimeSformer, i: int, x, descs, rows: int, save: bool, scales=None):
+    """timesformer.py:207-226.  x: [rows, C] bf16 tokens, (h w t) order.  scales: per-row DropPath factors
+    (temporal, spatial, mlp) of this block or None."""
     blk = model.blocks[i]
     C_, I = model.embed_dim, blk.mlp.fc1.weight.shape[0]
     dev, p = x.device, f"blocks.{i}."
     d_t, d_s = descs
-    # ---- temporal attention -> proj -> temporal_fc -> residual (:209-214)
+    s_t, s_s, s_m = scales if scales is not None else (None, None, None)
+    # ---- temporal attention -> proj -> drop_path -> temporal_fc -> residual (:209-214)
     ln_t, mean_t, rstd_t = _ln(x, blk.temporal_norm1, rows, C_, model.eps)
     qkv_t, a_t, lse_t = _attn_fwd(model, p + "temporal_attn.", blk.temporal_attn, ln_t, d_t, rows, C_)
     p_t = torch.empty(rows, C_, dtype=bf16, device=dev)
     ops.linear_fwd(a_t, _w(model, p + "temporal_attn.proj.weight", blk.temporal_attn.proj.weight),
                    blk.temporal_attn.proj.bias, p_t)
+    if s_t is not None:
+        ops.rowscale(p_t, s_t, p_t)          # in place: the saved p_t is the dropped one, as temporal_fc consumed it
     xt = torch.empty(rows, C_, dtype=bf16, device=dev)
     ops.linear_fwd(p_t, _w(model, p + "temporal_fc.weight", blk.temporal_fc.weight), blk.temporal_fc.bias, xt,
                    residual=x, ldr=C_)
     # ---- spatial attention -> proj -> residual (:216-224)
     ln_s, mean_s, rstd_s = _ln(xt, blk.norm1, rows, C_, model.eps)
     qkv_s, a_s, lse_s = _attn_fwd(model, p + "attn.", blk.attn, ln_s, d_s, rows, C_)
-    x2 = torch.empty(rows, C_, dtype=bf16, device=dev)
-    ops.linear_fwd(a_s, _w(model, p + "attn.proj.weight", blk.attn.proj.weight), blk.attn.proj.bias, x2,
-                   residual=xt, ldr=C_)
+    x2 = _residual_linear(model, p + "attn.proj", blk.attn.proj, a_s, xt, s_s, rows, C_)
     # ---- MLP with exact-erf GELU (:225, :132-138)
     ln_m, mean_m, rstd_m = _ln(x2, blk.norm2, rows, C_, model.eps)
     pre = torch.empty(rows, I, dtype=bf16, device=dev) if save else None
     f1 = torch.empty(rows, I, dtype=bf16, device=dev)
     ops.linear_fwd(ln_m, _w(model, p + "mlp.fc1.weight", blk.mlp.fc1.weight), blk.mlp.fc1.bias, f1,
                    act=_lib.ACT_GELU_ERF, aux=pre, ld_aux=I)
-    out = torch.empty(rows, C_, dtype=bf16, device=dev)
-    ops.linear_fwd(f1, _w(model, p + "mlp.fc2.weight", blk.mlp.fc2.weight), blk.mlp.fc2.bias, out, residual=x2, ldr=C_)
+    out = _residual_linear(model, p + "mlp.fc2", blk.mlp.fc2, f1, x2, s_m, rows, C_)
     saved = (x, mean_t, rstd_t, ln_t, qkv_t, a_t, lse_t, p_t, xt, mean_s, rstd_s, ln_s, qkv_s, a_s, lse_s, x2, mean_m,
              rstd_m, ln_m, pre, f1) if save else None
     return out, saved
@@ -204,7 +248,7 @@ def _linear_bwd(model, name: str, lin: nn.Linear, dy, x_in, grads, need_dx: bool
     return dx
 
 
-def _block_bwd(model: TimeSformer, i: int, dx, saved, descs, grads, rows: int):
+def _block_bwd(model: TimeSformer, i: int, dx, saved, descs, grads, rows: int, scales=None):
     (x, mean_t, rstd_t, ln_t, qkv_t, a_t, lse_t, p_t, xt, mean_s, rstd_s, ln_s, qkv_s, a_s, lse_s, x2, mean_m, rstd_m,
      ln_m, pre, f1) = saved
     blk = model.blocks[i]
@@ -225,17 +269,29 @@ def _block_bwd(model: TimeSformer, i: int, dx, saved, descs, grads, rows: int):
         ops.seg_attention_bwd(qkv, a, da, lse, delta, dqkv, desc, 0.125)
         return _linear_bwd(model, pre_name + "qkv", att.qkv, dqkv, h_in, grads)
 
-    # ---- out = x2 + fc2(gelu(fc1(LN(x2))))
-    dpre = _linear_bwd(model, p + "mlp.fc2", blk.mlp.fc2, dx, f1, grads, act=_lib.ACT_DGELU_ERF, aux=pre, ld_aux=I)
+    s_t, s_s, s_m = scales if scales is not None else (None, None, None)
+
+    def dropped(dy, s):     # gradient entering a drop_path'ed branch: the same per-row factor (one extra pass when active)
+        if s is None:
+            return dy
+        out = torch.empty_like(dy)
+        ops.rowscale(dy, s, out)
+        return out
+
+    # ---- out = x2 + drop_path(fc2(gelu(fc1(LN(x2)))))
+    dpre = _linear_bwd(model, p + "mlp.fc2", blk.mlp.fc2, dropped(dx, s_m), f1, grads, act=_lib.ACT_DGELU_ERF, aux=pre,
+                       ld_aux=I)
     dln_m = _linear_bwd(model, p + "mlp.fc1", blk.mlp.fc1, dpre, ln_m, grads)
     del dpre
     dx2 = ln_bwd(dln_m, x2, blk.norm2, p + "norm2", mean_m, rstd_m, dx)
-    # ---- x2 = xt + proj(attn_s(LN(xt)))
-    da_s = _linear_bwd(model, p + "attn.proj", blk.attn.proj, dx2, a_s, grads)
+    # ---- x2 = xt + drop_path(proj(attn_s(LN(xt))))
+    da_s = _linear_bwd(model, p + "attn.proj", blk.attn.proj, dropped(dx2, s_s), a_s, grads)
     dln_s = attn_bwd(p + "attn.", blk.attn, qkv_s, a_s, da_s, lse_s, ln_s, d_s)
     dxt = ln_bwd(dln_s, xt, blk.norm1, p + "norm1", mean_s, rstd_s, dx2)
-    # ---- xt = x + temporal_fc(proj_t(attn_t(LN(x))))
+    # ---- xt = x + temporal_fc(drop_path(proj_t(attn_t(LN(x)))))   (the saved p_t is already the dropped one)
     dp_t = _linear_bwd(model, p + "temporal_fc", blk.temporal_fc, dxt, p_t, grads)
+    if s_t is not None:
+        ops.rowscale(dp_t, s_t, dp_t)
     da_t = _linear_bwd(model, p + "temporal_attn.proj", blk.temporal_attn.proj, dp_t, a_t, grads)
     dln_t = attn_bwd(p + "temporal_attn.", blk.temporal_attn, qkv_t, a_t, da_t, lse_t, ln_t, d_t)
     return ln_bwd(dln_t, x, blk.temporal_norm1, p + "temporal_norm1", mean_t, rstd_t, dxt)
@@ -243,26 +299,27 @@ def _block_bwd(model: TimeSformer, i: int, dx, saved, descs, grads, rows: int):
 
 class _TimeSformerFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model: TimeSformer, names: List[str], x: torch.Tensor, *params):
+    def forward(ctx, model: TimeSformer, names: List[str], masks, x: torch.Tensor, *params):
         B, T, C_, H, W = x.shape
         if C_ != model.embed_dim:
             raise ValueError(f"expected {model.embed_dim} channels, got {C_}")
         HW, rows = H * W, B * H * W * T
-        save = any(ctx.needs_input_grad[2:])
+        save = any(ctx.needs_input_grad[3:])
         x = x.contiguous()
         pos_tab, time_tab = _tables(model, T, H, W)
         tok = torch.empty(rows, C_, dtype=bf16, device=x.device)
         ops.tsf_embed_fwd(x, pos_tab, time_tab, tok, B, T, C_, HW)
         descs = (ops.temporal_desc(rows, T, model.num_heads, 3 * C_, C_),
                  ops.spatial_desc(B, T, HW, model.num_heads, 3 * C_, C_))
+        scales = [_row_scales(None if masks is None else masks[i], B, T, HW) for i in range(model.depth)]
         saved = []
         for i in range(model.depth):
-            tok, sv = _block_fwd(model, i, tok, descs, rows, save)
+            tok, sv = _block_fwd(model, i, tok, descs, rows, save, scales[i])
             saved.append(sv)
         out = torch.empty(B, T, C_, H, W, dtype=x.dtype, device=x.device)   # timesformer.py:523 (values; contiguous)
         ops.tsf_untokenize(tok, out, B, T, C_, HW)
         if save:
-            ctx.model, ctx.names, ctx.saved, ctx.descs = model, names, saved, descs
+            ctx.model, ctx.names, ctx.saved, ctx.descs, ctx.scales = model, names, saved, descs, scales
             ctx.dims = (B, T, C_, H, W)
             ctx.x_dtype = x.dtype
         return out
@@ -279,10 +336,10 @@ class _TimeSformerFunction(torch.autograd.Function):
         for i in reversed(range(model.depth)):
             shapes = {n: tuple(p.shape) for n, p in model.blocks[i].named_parameters(prefix=f"blocks.{i}")}
             _alloc_flat(shapes, grads, dev)
-            dtok = _block_bwd(model, i, dtok, saved[i], descs, grads, rows)
+            dtok = _block_bwd(model, i, dtok, saved[i], descs, grads, rows, ctx.scales[i])
             saved[i] = None
         dx = None
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[3]:
             dx = torch.empty(B, T, C_, H, W, dtype=ctx.x_dtype, device=dev)
             ops.tsf_untokenize(dtok, dx, B, T, C_, HW)
         # table gradients: column sums of the token gradient over the broadcast dimensions
@@ -298,4 +355,4 @@ class _TimeSformerFunction(torch.autograd.Function):
             grads["pos_embed"], grads["time_embed"] = torch.autograd.grad(
                 [pos_tab, time_tab], [pp, tp], [d_pos_tab, d_time_tab.view(T, C_)])
         ctx.saved = None
-        return (None, None, dx) + tuple(grads[n] if ctx.needs_input_grad[3 + j] else None for j, n in enumerate(names))
+        return (None, None, None, dx) + tuple(grads[n] if ctx.needs_input_grad[4 + j] else None for j, n in enumerate(names))

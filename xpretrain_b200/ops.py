@@ -282,5 +282,12 @@ def tsf_embed_fwd(x, pos, time, tokens, B, T, C_, HW):
           "xp_tsf_embed_fwd")
 
 
+def rowscale(x, scale, out, residual=None):
+    """out = (residual or 0) + scale[:, None] * x  (DropPath on a residual branch); out may alias x."""
+    rows, C_ = x.shape
+    assert scale.dtype == f32 and scale.numel() == rows and x.is_contiguous() and out.is_contiguous()
+    check(lib().xp_rowscale_bf16(_p(x), _p(scale), _p(residual), _p(out), rows, C_, _stream()), "xp_rowscale_bf16")
+
+
 def tsf_untokenize(tokens, x, B, T, C_, HW):
     check(lib().xp_tsf_untokenize(_p(tokens), _p(x), _DT[x.dtype], B, T, C_, HW, _stream()), "xp_tsf_untokenize")
