@@ -380,7 +380,8 @@ vip_attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16
 }
 
 __global__ void __launch_bounds__(TB_THREADS, 1)
-vip_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+vip_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_f, const __grid_constant__ CUtensorMap tm_qkv_g,
+                       const __grid_constant__ CUtensorMap tm_do_f, const __grid_constant__ CUtensorMap tm_do_g,
                        const float* __restrict__ lse, const float* __restrict__ delta,
                        __nv_bfloat16* __restrict__ dqkv, float* __restrict__ gpart, const TcDims d, float q_scale) {
   extern __shared__ uint8_t smem_raw[];
@@ -404,7 +405,7 @@ vip_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat1
   const int total = d.B * d.H * d.T;
 
   if (tid == 0) {
-    mbar_init(full, 4);
+    mbar_init(full, 3);              // TMA expect_tx arrival + the two statistics warps
     mbar_init(smem_free, 1);
     mbar_init(sd_ready, 1);
     mbar_init(pds_ready, 256);
@@ -428,29 +429,31 @@ vip_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat1
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
                  tdQ = tmem_base + 384;
 
-  if (warp == 0 || warp == 2 || warp == 3 || warp == 12) {
+  if (warp == 0 || warp == 12) {
     // ----------------------------------------------------------------------------------- producers
-    const int role = warp == 0 ? 0 : (warp == 12 ? 1 : warp);   // 0: Q (+lse), 1: dO (+delta), 2: K, 3: V
-    const int chunk = lane & 7, r0 = lane >> 3;
+    // warp 0 lane 0: eight TMA box loads per problem — the L frame rows and the M global rows of the Q', K', V' head
+    // slices of qkv and of dO — land in the 128B-swizzled tiles the UMMA descriptors read (padding rows stay zero from
+    // the initial clear); warps 0 / 12 also stage lse * log2(e) / delta of the query rows.
+    const int role = warp == 0 ? 0 : 1;
     int n = 0;
     for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
       const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
       mbar_wait(smem_free, (n & 1) ^ 1);
       const long long tok_g = static_cast<long long>(b) * d.S, tok_f = tok_g + d.M + static_cast<long long>(t) * d.L;
-      if (role == 1) {
-        const __nv_bfloat16* src = dout + h * TC_HD + chunk * 8;
-        for (int row = r0; row < d.L; row += 4) tc_cp_async16(sw128(base + TB_SDO, row, chunk), src + (tok_f + row) * d.ld_o);
-        for (int row = r0; row < d.M; row += 4)
-          tc_cp_async16(sw128(base + TB_SDO + TC_GROW * 128, row, chunk), src + (tok_g + row) * d.ld_o);
-      } else {
-        const int mat = role == 0 ? 0 : role - 1;
-        const uint32_t dstF = base + (mat == 0 ? TB_SQ : (mat == 1 ? TB_SK : TB_SV));
-        const uint32_t dstG = base + (mat == 0 ? TB_SQ + TC_GROW * 128 : (mat == 1 ? TB_SKG : TB_SVG));
-        const __nv_bfloat16* src = qkv + mat * d.C + h * TC_HD + chunk * 8;
-        for (int row = r0; row < d.L; row += 4) tc_cp_async16(sw128(dstF, row, chunk), src + (tok_f + row) * d.ld_qkv);
-        for (int row = r0; row < d.M; row += 4) tc_cp_async16(sw128(dstG, row, chunk), src + (tok_g + row) * d.ld_qkv);
+      if (role == 0 && lane == 0) {
+        mbar_arrive_expect_tx(full, 4u * static_cast<uint32_t>(d.L + d.M) * 128u);
+        const int rf = static_cast<int>(tok_f), rg = static_cast<int>(tok_g);
+        const int cq = h * TC_HD, ck = d.C + h * TC_HD, cv = 2 * d.C + h * TC_HD;
+        tma_load_2d(gbase + TB_SQ, &tm_qkv_f, full, cq, rf);
+        tma_load_2d(gbase + TB_SQ + TC_GROW * 128, &tm_qkv_g, full, cq, rg);
+        tma_load_2d(gbase + TB_SDO, &tm_do_f, full, cq, rf);
+        tma_load_2d(gbase + TB_SDO + TC_GROW * 128, &tm_do_g, full, cq, rg);
+        tma_load_2d(gbase + TB_SK, &tm_qkv_f, full, ck, rf);
+        tma_load_2d(gbase + TB_SKG, &tm_qkv_g, full, ck, rg);
+        tma_load_2d(gbase + TB_SV, &tm_qkv_f, full, cv, rf);
+        tma_load_2d(gbase + TB_SVG, &tm_qkv_g, full, cv, rg);
       }
-      if (role <= 1) {   // per-row statistics of the query rows: lse * log2(e) (+inf on padding rows) / delta
+      {   // per-row statistics of the query rows: lse * log2(e) (+inf on padding rows) / delta
         const float* src = (role == 0 ? lse : delta) + (static_cast<long long>(b) * d.H + h) * d.S;
         float* dst = role == 0 ? s_lse : s_del;
         for (int row = lane; row < 256; row += 32) {
@@ -460,8 +463,6 @@ vip_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat1
           dst[row] = v;
         }
       }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full);
     }
@@ -565,13 +566,18 @@ vip_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat1
           tc_fence_after();
           const float l2 = s_lse[row], dl = s_del[row];   // +inf lse on padding rows -> P = 0
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {                    // 16 key columns per iteration
+          for (int c2 = 0; c2 < 2; ++c2) {                 // 32 key columns per TMEM load pair
+            uint32_t rs32[32], rp32[32];
+            tmem_ld32(tS + lane_off + wg * 64 + c2 * 32, rs32);
+            tmem_ld32(tdP + lane_off + wg * 64 + c2 * 32, rp32);
+            tmem_ld_wait(rs32);
+            tmem_ld_wait(rp32);
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {                 // 16 key columns = two 16-byte chunks of P and of dS
+            const int c = c2 * 2 + ch;
             const int col0 = wg * 64 + c * 16;
-            uint32_t rs[16], rp[16];
-            tmem_ld16(tS + lane_off + col0, rs);
-            tmem_ld16(tdP + lane_off + col0, rp);
-            tmem_ld_wait16(rs);
-            tmem_ld_wait16(rp);
+            const uint32_t* rs = rs32 + ch * 16;
+            const uint32_t* rp = rp32 + ch * 16;
             uint32_t pk[8], dk[8];
 #pragma unroll
             for (int e = 0; e < 16; e += 2) {
@@ -599,6 +605,7 @@ vip_attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat1
                          "r"(dk[2]), "r"(dk[3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdS, trow, 2 * c + 1)), "r"(dk[4]),
                          "r"(dk[5]), "r"(dk[6]), "r"(dk[7]) : "memory");
+          }
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -713,9 +720,14 @@ extern "C" int xp_vip_attention_bwd_tc_partial(const void* qkv, const void* out,
   }
   const long long total = static_cast<long long>(B) * H * T;
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+  // TMA boxes: 64 columns (one head slice) x L frame rows / x M global rows of the token-major buffers
+  CUtensorMap tm_qkv_f, tm_qkv_g, tm_do_f, tm_do_g;
+  if (make_tmap_bf16_2d(&tm_qkv_f, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, L)) return -1;
+  if (make_tmap_bf16_2d(&tm_qkv_g, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, M)) return -1;
+  if (make_tmap_bf16_2d(&tm_do_f, dout, C, rows, d.ld_o, TC_HD, L)) return -1;
+  if (make_tmap_bf16_2d(&tm_do_g, dout, C, rows, d.ld_o, TC_HD, M)) return -1;
   vip_attn_bwd_tc_kernel<<<grid, TB_THREADS, smem, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-      static_cast<__nv_bfloat16*>(dqkv), workspace, d, q_scale);
+      tm_qkv_f, tm_qkv_g, tm_do_f, tm_do_g, lse, delta, static_cast<__nv_bfloat16*>(dqkv), workspace, d, q_scale);
   XP_CHECK_LAUNCH("vip_attn_bwd_tc_kernel");
   return 0;
 }

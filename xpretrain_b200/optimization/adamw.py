@@ -145,7 +145,8 @@ class AdamW(Optimizer):
             if tab is None:
                 tab = self._tables[key] = _Table([p.numel() for p, _ in items], dev)
             rows = tab.begin()
-            for i, (p, group) in enumerate(items):
+            sizes, decays = [], []
+            for p, group in items:
                 state = self.state[p]
                 if len(state) == 0:                          # adamw.py:64-70
                     state["step"] = 0
@@ -156,10 +157,16 @@ class AdamW(Optimizer):
                 step_size = group["lr"]
                 if group["correct_bias"]:                    # adamw.py:85-89
                     step_size = step_size * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
-                tgt = self.bf16_targets.get(id(p))
-                rows[i] = (p.data_ptr(), p.grad.data_ptr(), state["exp_avg"].data_ptr(), state["exp_avg_sq"].data_ptr(),
-                           tgt.data_ptr() if tgt is not None else 0, p.numel(), step_size,
-                           group["lr"] * group["weight_decay"] if group["weight_decay"] > 0.0 else 0.0, (0, 0))
+                sizes.append(step_size)
+                decays.append(group["lr"] * group["weight_decay"] if group["weight_decay"] > 0.0 else 0.0)
+            # column-wise fills of the pinned table (one numpy assignment per field, not one tuple per parameter)
+            rows["p"] = [p.data_ptr() for p, _ in items]
+            rows["g"] = [p.grad.data_ptr() for p, _ in items]
+            rows["m"] = [self.state[p]["exp_avg"].data_ptr() for p, _ in items]
+            rows["v"] = [self.state[p]["exp_avg_sq"].data_ptr() for p, _ in items]
+            rows["pb"] = [self.bf16_targets[id(p)].data_ptr() if id(p) in self.bf16_targets else 0 for p, _ in items]
+            rows["step_size"] = sizes
+            rows["decay"] = decays
             tab.upload()
             norm_ptr = None
             if max_grad_norm is not None:
