@@ -180,6 +180,12 @@ int xp_text_attention_bwd(const void* qkv, const void* dout, const float* probs,
 int xp_nce_split(const float* x, void* x3_bf16, void* hi_bf16, int32_t rows, int32_t d, int32_t pattern, void* stream);
 int xp_nce_softmax_grad(const float* z, const float* logit_scale, float* lse_rows, float* lse_cols, void* g_scaled_bf16,
                         float* loss, float* d_logit_scale, int32_t N, int64_t ld, void* stream);
+/* NCELearnableTempLoss_vsc_fc.forward, CLIP-ViP/src/optimization/loss.py:288-324 (the released pre-training default:
+ * video x subtitle, video x caption, frame x caption): za = V T^T, zb = V C^T, zd = I C^T, fp32 [N, N] with row pitch ld,
+ * unscaled.  Writes the scalar loss (overwritten), ACCUMULATES d_logit_scale, and the three gradient matrices
+ * g* = exp(logit_scale) * dL/d(s z*) as bf16 [N, N] (row pitch ld).  stats: 6*N floats of scratch. */
+int xp_nce_vsc_fc(const float* za, const float* zb, const float* zd, const float* logit_scale, float* stats, void* ga_bf16,
+                  void* gb_bf16, void* gd_bf16, float* loss, float* d_logit_scale, int32_t N, int64_t ld, void* stream);
 
 /* ---- BASELINE.json config #4: HD-VILA TimeSformer (divided space-time attention), hd-vila/src/modeling/timesformer.py
  *

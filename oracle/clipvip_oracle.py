@@ -235,6 +235,26 @@ def nce_closed_form_grads(vis: Tensor, txt: Tensor, logit_scale: Tensor):
     return s * g @ txt, s * g.t() @ vis, (g * z).sum()
 
 
+def nce_vsc_fc_loss(vis: Tensor, txt: Tensor, img: Tensor, cap: Tensor, logit_scale: Tensor) -> Tensor:
+    """NCELearnableTempLoss_vsc_fc.forward, loss.py:288-324 (the released pre-training default, pretrain_vip_base_16.json:74-77):
+    six cross-entropies over A = s V T^T (video x subtitle), B = s V C^T (video x caption), D = s I C^T (frame x caption):
+      columns of A, columns of B                                    (t2v, t2v_2:  :296-301, :316)
+      row i over [A_ii | A_i,j!=i | B_i,j!=i] and [B_ii | A_i,j!=i | B_i,j!=i] with label 0   (:303-310, :317)
+      columns and rows of D                                         (:312-318)
+    each a mean over the N rows, summed."""
+    s = logit_scale.exp()
+    a, b, d = vis @ txt.t() * s, vis @ cap.t() * s, img @ cap.t() * s
+    n = a.shape[0]
+    eye = torch.eye(n, dtype=torch.bool, device=a.device)
+    ninf = torch.full_like(a, float("-inf"))
+    row3 = torch.logsumexp(torch.cat([a, torch.where(eye, ninf, b)], 1), 1)      # A row (all) + B row without its diagonal
+    row4 = torch.logsumexp(torch.cat([torch.where(eye, ninf, a), b], 1), 1)      # A row without its diagonal + B row (all)
+    da, db, dd = a.diagonal(), b.diagonal(), d.diagonal()
+    terms = (torch.logsumexp(a, 0) - da, torch.logsumexp(b, 0) - db, row3 - da, row4 - db,
+             torch.logsumexp(d, 0) - dd, torch.logsumexp(d, 1) - dd)
+    return sum(t.mean() for t in terms)
+
+
 def gather_rank_major(per_rank: list) -> Tensor:
     """hvd.allgather (run_pretrain.py:344-345) / SyncFunction.forward (LF-VILA/src/utils/dist.py:21-33):
     rank-major concatenation along dim 0."""

@@ -128,7 +128,36 @@ def loss_case():
     print("[nce_loss_w4] closed-form gradients match autograd of the reference loss")
 
 
+def vsc_fc_loss_case():
+    """The released pre-training default loss (pretrain_vip_base_16.json:74-77): NCELearnableTempLoss_vsc_fc, loss.py:288-324."""
+    from src.optimization.loss import NCELearnableTempLoss_vsc_fc
+
+    g = torch.Generator().manual_seed(11)
+    N, d = 24, 512
+    feats = [torch.nn.functional.normalize(torch.randn(N, d, generator=g), dim=-1).requires_grad_(True) for _ in range(4)]
+    temp = torch.tensor(4.6, requires_grad=True)
+    loss = NCELearnableTempLoss_vsc_fc(None)(*feats, temp)
+    loss.backward()
+    ref_grads = [f.grad.clone() for f in feats] + [temp.grad.clone()]
+    f2 = [f.detach().clone().requires_grad_(True) for f in feats]
+    t2 = temp.detach().clone().requires_grad_(True)
+    lo = O.nce_vsc_fc_loss(*f2, t2)
+    lo.backward()
+    assert abs(float(lo) - float(loss)) < 1e-5 * abs(float(loss))
+    for a, b in zip([f.grad for f in f2] + [t2.grad], ref_grads):
+        assert rel(a, b) < 1e-5
+    torch.save({"vis": feats[0].detach(), "txt": feats[1].detach(), "img": feats[2].detach(), "cap": feats[3].detach(),
+                "logit_scale": temp.detach(), "loss": loss.detach(), "d_vis": ref_grads[0], "d_txt": ref_grads[1],
+                "d_img": ref_grads[2], "d_cap": ref_grads[3], "d_logit_scale": ref_grads[4]},
+               os.path.join(HERE, "nce_vsc_fc_n24.pt"))
+    print("[nce_vsc_fc_n24] oracle restatement matches the reference loss and its autograd gradients")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":      # regenerate only the (cheap) loss fixtures
+        loss_case()
+        vsc_fc_loss_case()
+        sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
     full = O.ClipVipCfg()

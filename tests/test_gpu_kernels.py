@@ -322,3 +322,36 @@ def test_nce_loss_and_grads(dev, N):
     assert abs(float(got) - float(want)) < 2e-4 * max(1.0, abs(float(want)))
     assert rel(vd.grad.cpu(), vr.grad) < 6e-3 and rel(td.grad.cpu(), tr.grad) < 6e-3
     assert abs(float(pd.grad) - float(pr.grad)) < 2e-3 * max(1.0, abs(float(pr.grad)))
+
+
+@pytest.mark.parametrize("N", [24, 512, 20])
+def test_nce_vsc_fc_loss_and_grads(dev, N, golden_dir):
+    """The released pre-training default loss (loss.py:288-324): six-term video/subtitle/caption/frame InfoNCE."""
+    import os
+
+    from oracle import clipvip_oracle as O
+    from xpretrain_b200.optimization import build_loss_func
+    if N == 24:      # the fixture written from the reference's own class and autograd
+        gold = torch.load(os.path.join(golden_dir, "nce_vsc_fc_n24.pt"), weights_only=False)
+        feats, temp = [gold[k] for k in ("vis", "txt", "img", "cap")], gold["logit_scale"]
+        want_loss, want_grads = gold["loss"], [gold[k] for k in ("d_vis", "d_txt", "d_img", "d_cap")]
+        want_dscale = gold["d_logit_scale"]
+    else:
+        g = torch.Generator(device="cpu").manual_seed(N)
+        base = F.normalize(torch.randn(N, 512, generator=g), dim=-1)
+        feats = [F.normalize(torch.randn(N, 512, generator=g) + 0.5 * base, dim=-1) for _ in range(4)]
+        temp = torch.tensor(4.6)
+        fr = [f.clone().requires_grad_(True) for f in feats]
+        pr = temp.clone().requires_grad_(True)
+        want_loss = O.nce_vsc_fc_loss(*fr, pr)
+        want_loss.backward()
+        want_grads, want_dscale = [f.grad for f in fr], pr.grad
+    fd = [f.to(dev).requires_grad_(True) for f in feats]
+    pd = temp.to(dev).requires_grad_(True)
+    loss_fn = build_loss_func({"loss_name": "NCELearnableTempLoss_vsc_fc"})
+    got = loss_fn(*fd, pd)
+    got.backward()
+    assert abs(float(got) - float(want_loss)) < 2e-4 * max(1.0, abs(float(want_loss)))
+    for a, b in zip(fd, want_grads):
+        assert rel(a.grad.cpu(), b) < 6e-3
+    assert abs(float(pd.grad) - float(want_dscale)) < 2e-3 * max(1.0, abs(float(want_dscale)))

@@ -196,3 +196,15 @@ def test_timesformer_oracle_training_mode_drop_path_golden(golden_dir):
     for n, ref in gold["grads"].items():
         got = sd[n].grad[:8] if ref.dim() == 2 else sd[n].grad
         assert float((got - ref).norm()) < 1e-4 * gold["grad_norms"][n] + 1e-9, n
+
+
+def test_nce_vsc_fc_oracle_replays_reference_golden(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "nce_vsc_fc_n24.pt"), weights_only=False)
+    feats = [gold[k].clone().requires_grad_(True) for k in ("vis", "txt", "img", "cap")]
+    temp = gold["logit_scale"].clone().requires_grad_(True)
+    loss = O.nce_vsc_fc_loss(*feats, temp)
+    loss.backward()
+    assert abs(float(loss) - float(gold["loss"])) < 1e-5 * abs(float(gold["loss"]))
+    for f, k in zip(feats, ("d_vis", "d_txt", "d_img", "d_cap")):
+        assert _rel(f.grad, gold[k]) < 1e-5
+    assert abs(float(temp.grad) - float(gold["d_logit_scale"])) < 1e-5 * abs(float(gold["d_logit_scale"]))

@@ -85,7 +85,9 @@ SIGNATURES = {
     "xp_nce_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "xp_nce_softmax_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_i64, c_void_p]),
-    "xp_seg_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, P(XpSegAttn), c_void_p]),
+    "xp_nce_vsc_fc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_int, c_i64, c_void_p]),
+    "xp_seg_attention_fwd":(c_int, [c_void_p, c_void_p, c_void_p, P(XpSegAttn), c_void_p]),
     "xp_seg_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, P(XpSegAttn), c_float,
                                      c_void_p]),
     "xp_tsf_embed_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

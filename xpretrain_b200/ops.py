@@ -245,6 +245,13 @@ def nce_softmax_grad(z, logit_scale, lse_r, lse_c, g_scaled, loss, d_logit_scale
                                     _p(d_logit_scale), N, ld, _stream()), "xp_nce_softmax_grad")
 
 
+def nce_vsc_fc(za, zb, zd, logit_scale, stats, ga, gb, gd, loss, d_logit_scale):
+    N, ld = za.shape[0], za.stride(0)
+    assert zb.stride(0) == ld and zd.stride(0) == ld and ga.stride(0) == ld and stats.numel() >= 6 * N
+    check(lib().xp_nce_vsc_fc(_p(za), _p(zb), _p(zd), _p(logit_scale), _p(stats), _p(ga), _p(gb), _p(gd), _p(loss),
+                              _p(d_logit_scale), N, ld, _stream()), "xp_nce_vsc_fc")
+
+
 # ------------------------------------------------------------- config #4: TimeSformer (HD-VILA)
 def seg_desc(n_rows: int, heads: int, ld_qkv: int, ld_out: int, *, n_seq: int, seq_len: int, seg_len: int, inner: int,
              outer_stride: int, inner_stride: int, tok_stride: int) -> XpSegAttn:

@@ -130,7 +130,75 @@ def gather_nce_loss(vis_feat, text_feat, temp, group=None, grad_scale: Optional[
     return _GatherNceFunction.apply(vis_feat, text_feat, temp, group, grad_scale)
 
 
-_LOSSES = {"NCELearnableTempLoss": NCELearnableTempLoss}
+def _split_hi(x: torch.Tensor, rows_pad: int, pattern: int):
+    """bf16 hi/lo split of an fp32 [N, d] matrix: ([rows_pad, 3d] K-concatenated operand, [N, d] hi copy)."""
+    N, d = x.shape
+    x3 = (torch.zeros if rows_pad != N else torch.empty)(rows_pad, 3 * d, dtype=bf16, device=x.device)
+    hi = torch.empty(N, d, dtype=bf16, device=x.device)
+    ops.nce_split(x.contiguous(), x3, hi, pattern)
+    return x3, hi
+
+
+class _NceVscFcFunction(torch.autograd.Function):
+    """NCELearnableTempLoss_vsc_fc (loss.py:288-324): three hi/lo-split tcgen05 logits GEMMs (V T^T, V C^T, I C^T), the
+    six-term softmax / loss / dL/dZ kernels of nce.cu, and six gradient GEMMs in backward."""
+
+    @staticmethod
+    def forward(ctx, vis, txt, img, cap, temp):
+        assert txt.shape[0] == cap.shape[0]                                   # loss.py:290
+        N, d = vis.shape
+        Np, dev = _pad8(N), vis.device
+        v3, vh = _split_hi(vis.to(f32), N, 0)
+        i3, ih = _split_hi(img.to(f32), N, 0)
+        t3, th = _split_hi(txt.to(f32), Np, 1)
+        c3, ch = _split_hi(cap.to(f32), Np, 1)
+        z = torch.empty(3, N, Np, dtype=f32, device=dev)
+        for k, (a, b) in enumerate(((v3, t3), (v3, c3), (i3, c3))):
+            ops.gemm(a, b, z[k], M=N, N=Np, K=3 * d, lda=3 * d, ldb=3 * d, ldc=Np, out_mode=_lib.OUT_F32)
+        g = torch.empty(3, N, Np, dtype=bf16, device=dev)
+        stats = torch.empty(6 * N, dtype=f32, device=dev)
+        loss = torch.empty(1, dtype=f32, device=dev)
+        dscale = torch.zeros(1, dtype=f32, device=dev)
+        ops.nce_vsc_fc(z[0], z[1], z[2], temp.detach().reshape(1).to(f32), stats, g[0], g[1], g[2], loss, dscale)
+        ctx.saved = (g, vh, th, ih, ch, dscale)
+        ctx.in_meta = (vis.dtype, txt.dtype, img.dtype, cap.dtype, temp.dtype, temp.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        g, vh, th, ih, ch, dscale = ctx.saved
+        N, d = vh.shape
+        Np, dev = g.shape[2], g.device
+        out = torch.zeros(4, N, d, dtype=f32, device=dev)                     # d_vis, d_txt, d_img, d_cap (atomic accumulation)
+
+        def rows_times(gk, feat, dst):       # dst += G_k  @ feat   (A = G_k rows, K-major; B = feat [K=N, d] MN-major)
+            ops.gemm(gk, feat, dst, M=N, N=d, K=N, lda=Np, ldb=d, ldc=d, b_layout=1, out_mode=_lib.OUT_F32_ATOMIC)
+
+        def cols_times(gk, feat, dst):       # dst += G_k^T @ feat  (A = G_k^T: MN-major)
+            ops.gemm(gk, feat, dst, M=N, N=d, K=N, lda=Np, ldb=d, ldc=d, a_layout=1, b_layout=1,
+                     out_mode=_lib.OUT_F32_ATOMIC)
+
+        rows_times(g[0], th, out[0]); rows_times(g[1], ch, out[0])            # dV = s (G_a T + G_b C)
+        cols_times(g[0], vh, out[1])                                          # dT = s G_a^T V
+        rows_times(g[2], ch, out[2])                                          # dI = s G_d C
+        cols_times(g[1], vh, out[3]); cols_times(g[2], ih, out[3])            # dC = s (G_b^T V + G_d^T I)
+        vd, td, idt, cd, pd, pshape = ctx.in_meta
+        return ((out[0] * dloss).to(vd), (out[1] * dloss).to(td), (out[2] * dloss).to(idt), (out[3] * dloss).to(cd),
+                (dscale * dloss).reshape(pshape).to(pd))
+
+
+class NCELearnableTempLoss_vsc_fc(nn.Module):
+    """Drop-in for loss.py:280-324 — the released pre-training default (pretrain_vip_base_16.json:74-77):
+    forward(vis_feat, text_feat, img_feat, cap_feat, temp) on the (gathered) feature matrices."""
+
+    def __init__(self, cfg=None):
+        super().__init__()
+
+    def forward(self, vis_feat, text_feat, img_feat, cap_feat, temp):
+        return _NceVscFcFunction.apply(vis_feat, text_feat, img_feat, cap_feat, temp)
+
+
+_LOSSES = {"NCELearnableTempLoss": NCELearnableTempLoss, "NCELearnableTempLoss_vsc_fc": NCELearnableTempLoss_vsc_fc}
 
 
 def build_loss_func(cfg):
