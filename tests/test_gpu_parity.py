@@ -158,3 +158,42 @@ def test_state_dict_round_trip(dev):
     assert set(own) == {"clipmodel." + k for k in sd}
     for k, v in sd.items():
         assert own["clipmodel." + k].shape == v.shape and own["clipmodel." + k].dtype == v.dtype, k
+
+
+def test_image_caption_branch_and_vsc_fc_loss_against_oracle(dev):
+    """The released pre-training path (VidCLIP.py:70-79 + loss.py:288-324): video/subtitle pass plus a T = 1 frame/caption
+    pass through the same towers (temporal table interpolated 12 -> 1), six-term loss, backward through both passes."""
+    from oracle import clipvip_oracle as O
+    from xpretrain_b200.optimization.loss import build_loss_func
+    cfg = O.ClipVipCfg(vision=O.TowerCfg(768, 12, 1, 3072), text=O.TowerCfg(512, 8, 1, 2048))
+    sd = O.init_state_dict(cfg, seed=5)
+    B, T, Lt = 4, 2, 16
+    video, ids, mask = O.synthetic_batch(B, T, Lt, cfg, seed=21)
+    image, cap_ids, cap_mask = O.synthetic_batch(B, 1, Lt, cfg, seed=22, ragged_text=True)
+    model = _build(cfg, sd, dev)
+    out = model(video=video.to(dev), text_input_ids=ids.to(dev), text_input_mask=mask.to(dev), image=image.to(dev),
+                caption_ids=cap_ids.to(dev), caption_masks=cap_mask.to(dev))
+    assert set(out) == {"text_features", "vis_features", "img_features", "cap_features"}
+    loss_fn = build_loss_func({"loss_name": "NCELearnableTempLoss_vsc_fc"})
+    loss = loss_fn(out["vis_features"], out["text_features"], out["img_features"], out["cap_features"],
+                   model.clipmodel.logit_scale)
+    loss.backward()
+    # oracle (fp32, host): the same two passes share the weights, gradients accumulate over both
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    o1 = O.clip_vip_forward(sdo, video, ids, mask, cfg)
+    o2 = O.clip_vip_forward(sdo, image.reshape(-1, 1, *image.shape[2:]), cap_ids, cap_mask, cfg)
+    want = O.nce_vsc_fc_loss(o1["vis_features"], o1["text_features"], o2["vis_features"], o2["text_features"],
+                             sdo["logit_scale"])
+    want.backward()
+    for k, ref in (("vis_features", o1["vis_features"]), ("text_features", o1["text_features"]),
+                   ("img_features", o2["vis_features"]), ("cap_features", o2["text_features"])):
+        assert _rel(out[k].detach().cpu(), ref.detach()) < EMB_REL_L2, k
+    assert abs(float(loss) - float(want)) < LOSS_REL * abs(float(want))
+    named = dict(model.clipmodel.named_parameters())
+    for k in ("vision_model.embeddings.temporal_embedding", "vision_model.encoder.layers.0.mlp.fc1.weight",
+              "text_model.encoder.layers.0.self_attn.q_proj.weight", "visual_projection.weight", "text_projection.weight",
+              "vision_model.embeddings.patch_embedding.weight"):
+        got, ref = named[k].grad.detach().flatten().cpu(), sdo[k].grad.flatten()
+        cos = float(torch.nn.functional.cosine_similarity(got, ref, dim=0))
+        assert cos > GRAD_COSINE, (k, cos)
+    assert abs(float(model.clipmodel.logit_scale.grad) - float(sdo["logit_scale"].grad)) < 0.05 * abs(float(sdo["logit_scale"].grad)) + 1e-3
