@@ -225,6 +225,18 @@ int xp_tsf_untokenize(const void* tokens_bf16, void* x, int32_t x_dtype, int32_t
 int xp_rowscale_bf16(const void* x, const float* scale, const void* residual, void* out, int64_t rows, int32_t C,
                      void* stream);
 
+/* ---- retrieval evaluation.  Replaces the numpy calls of validate() (CLIP-ViP/src/pretrain/
+ * run_pretrain.py:173-176, tasks/run_video_retrieval.py:155-172) on CLIP-ViP/src/utils/metrics.py:
+ *   xp_sim_f32      cal_cossim (:3-5): out[Na, Nb] (row pitch ld) = a[Na, d] b[Nb, d]^T, fp32 FFMA accumulation
+ *   xp_dsl_reweight sim *= softmax(theta * sim, axis=0) in place (np_softmax :7-39 as used at run_video_retrieval.py:169-170);
+ *                   col_scratch: 2*cols floats
+ *   xp_rank_counts  compute_metrics' rank search (:41-48) without the sort: greater[i] / equal[i] = number of entries of row i
+ *                   (transpose != 0: column i) strictly larger than / equal to sim[i, i]; the reference's rank list is
+ *                   {greater[i] + t : 0 <= t < equal[i]} (ties counted once per tied entry, as np.where(ind == 0) does). */
+int xp_sim_f32(const float* a, const float* b, float* out, int32_t Na, int32_t Nb, int32_t d, int64_t ld, void* stream);
+int xp_dsl_reweight(float* sim, int32_t rows, int32_t cols, int64_t ld, float theta, float* col_scratch, void* stream);
+int xp_rank_counts(const float* sim, int32_t N, int64_t ld, int32_t transpose, int32_t* greater, int32_t* equal, void* stream);
+
 /* ---- the optimizer step.  Replaces AdamW.step (CLIP-ViP/src/optimization/adamw.py:40-103) and
  * torch.nn.utils.clip_grad_norm_ as called at pretrain/run_pretrain.py:408-411,422 — one table-driven launch over all
  * parameters instead of ~10 elementwise launches per parameter.

@@ -208,3 +208,22 @@ def test_nce_vsc_fc_oracle_replays_reference_golden(golden_dir):
     for f, k in zip(feats, ("d_vis", "d_txt", "d_img", "d_cap")):
         assert _rel(f.grad, gold[k]) < 1e-5
     assert abs(float(temp.grad) - float(gold["d_logit_scale"])) < 1e-5 * abs(float(gold["d_logit_scale"]))
+
+
+def test_retrieval_metrics_oracle_replays_reference_golden(golden_dir):
+    """§8(f).3: similarity, DSL re-weighting and compute_metrics (with its tie quirk) vs the reference's own numpy code."""
+    import numpy as np
+    from oracle import metrics_oracle as MO
+
+    gold = torch.load(os.path.join(golden_dir, "retrieval_metrics_n57.pt"), weights_only=False)
+    txt, vis = gold["txt"].numpy(), gold["vis"].numpy()
+    sim = MO.cal_cossim(txt, vis)
+    assert np.allclose(sim, gold["sim"].numpy(), rtol=0, atol=1e-6)       # BLAS summation order may differ between hosts
+    sim = gold["sim"].numpy()                                             # integer logic below: on the stored matrix, exact
+    for kind, m in (("simple", sim), ("DSL", MO.dsl(sim, 100.0))):
+        for direction, x in (("t2v", m), ("v2t", m.T)):
+            g, e = MO.rank_counts(x)
+            assert np.array_equal(g, gold[f"{kind}_{direction}_greater"].numpy()), (kind, direction)
+            assert np.array_equal(e, gold[f"{kind}_{direction}_equal"].numpy())
+            assert tuple(float(v) for v in MO.compute_metrics(x)) == gold[f"{kind}_{direction}"]
+    assert int(gold["simple_t2v_equal"].max()) >= 2                       # the fixture really contains ties

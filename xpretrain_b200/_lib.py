@@ -92,7 +92,10 @@ SIGNATURES = {
                                      c_void_p]),
     "xp_tsf_embed_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xp_tsf_untokenize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "xp_rowscale_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "xp_sim_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_void_p]),
+    "xp_dsl_reweight": (c_int, [c_void_p, c_int, c_int, c_i64, c_float, c_void_p, c_void_p]),
+    "xp_rank_counts": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "xp_rowscale_bf16":(c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "xp_opt_chunk_elems": (c_int, []),
     "xp_opt_grad_norm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "xp_opt_scale_grads": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
