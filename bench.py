@@ -192,7 +192,7 @@ def run_ours(args):
                 t.record_stream(torch.cuda.current_stream())
             if i + 1 < steps:
                 ev = prefetch(i + 1)
-            last["loss"] = float(step(*batch))            # .item(): device -> host read of the step's result
+            last["loss"] = step(*batch).detach().item()   # device -> host read of the step's result
 
     e2e_loop(2)                                            # warm the copy path
     barrier()
