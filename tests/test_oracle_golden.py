@@ -227,3 +227,40 @@ def test_retrieval_metrics_oracle_replays_reference_golden(golden_dir):
             assert np.array_equal(e, gold[f"{kind}_{direction}_equal"].numpy())
             assert tuple(float(v) for v in MO.compute_metrics(x)) == gold[f"{kind}_{direction}"]
     assert int(gold["simple_t2v_equal"].max()) >= 2                       # the fixture really contains ties
+
+
+# ------------------------------------------------------------------ config #5: LF-VILA Swin-3D video encoder
+@pytest.mark.parametrize("name", ["swin3d_small_b2", "swin3d_padded_b1", "swin3d_train_droppath"])
+def test_swin3d_oracle_replays_reference_golden(golden_dir, name):
+    from oracle import swin3d_oracle as SO
+
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    cfg = SO.Swin3DCfg(**gold["cfg"])
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v)
+          for k, v in SO.init_state_dict(cfg, seed=gold["weight_seed"]).items()}
+    video = SO.synthetic_video(gold["B"], gold["D"], gold["H"], gold["W"], cfg, seed=gold["data_seed"])
+    if gold["train_rate"]:                       # the DropPath factors the reference drew are reproduced from its torch seed
+        torch.manual_seed(gold["torch_seed"])
+        masks = SO.draw_drop_masks(cfg, gold["B"], gold["train_rate"])
+        for a, b in zip(masks, gold["masks"]):
+            assert (a is None) == (b is None) and (a is None or all(torch.equal(u, v) for u, v in zip(a, b)))
+    out, stages = SO.swin3d_forward(sd, video, cfg, drop_masks=gold["masks"], return_stages=True)
+    assert out.shape == gold["out"].shape and _rel(out.detach(), gold["out"]) < 1e-5
+    for s, ref in zip(stages, gold["stage_rows"]):
+        assert _rel(s.flatten(0, 3)[:4].detach(), ref) < 1e-5
+    g = torch.Generator().manual_seed(gold["data_seed"] + 1)
+    w_out = torch.randn(out.shape, generator=g) / out[0].numel() ** 0.5
+    (out * w_out).sum().backward()
+    for n, ref in gold["grads"].items():
+        got = sd[n].grad[:8] if ref.dim() >= 2 else sd[n].grad
+        assert float((got - ref).norm()) < 1e-4 * gold["grad_norms"][n] + 1e-9, n
+    assert sd["norm_local.weight"].grad is None and sd["local_feat_proj.reduction.weight"].grad is None   # (x, x) quirk
+
+
+def test_swin3d_flop_and_parameter_model_matches_baseline_md():
+    from oracle import swin3d_oracle as SO
+
+    cfg = SO.Swin3DCfg()
+    assert sum(v.numel() for v in SO.init_state_dict(cfg).values() if v.is_floating_point()) == 89_229_448
+    assert abs(SO.flops_per_sample(cfg, 32, 224, 224, include_dead_local_proj=True) / 1e9 - 327.14) < 0.01
+    assert abs(SO.flops_per_sample(cfg, 32, 192, 320, include_dead_local_proj=True) / 1e9 - 313.63) < 0.01
