@@ -206,6 +206,21 @@ typedef struct XpSegAttn {
   int64_t ld_qkv, ld_out;
   int64_t outer_stride, inner_stride, tok_stride;
   int32_t heads, n_seq, seq_len, seg_len, inner, reserved;
+  /* Window-attention extensions — LF-VILA WindowAttention3D.forward, LF-VILA/src/models/video_encoder.py:135-164, together
+   * with the pad / roll / window_partition / window_reverse / crop around it (:214-243).  All optional (NULL / 0):
+   *   row_index    int32 [n_seq, seq_len]: token row of every window position (replaces the stride pattern; dense sequences).
+   *                Built once per feature-map shape by applying the reference's own pad/roll/partition to an index tensor;
+   *                zero-padded positions point at extra all-zero input rows, whose k, v are the qkv bias exactly as in the
+   *                reference.
+   *   bias         fp32 [bias_windows, heads, seq_len, seq_len] added to the logits before the softmax: relative-position
+   *                bias (+ the 0 / -100 shift mask of window type s % bias_windows)
+   *   ds_out       (bwd) bf16 [n_seq, heads, seq_len, seq_len]: dL/dlogits, whose sum over windows is the bias gradient
+   *   head_dim     64 (or 0) or 32 */
+  const int32_t* row_index;
+  const float* bias;
+  void* ds_out;
+  int32_t bias_windows;
+  int32_t head_dim;
 } XpSegAttn;
 int xp_seg_attention_fwd(const void* qkv, void* out, float* lse, const XpSegAttn* desc, void* stream);
 int xp_seg_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
@@ -224,6 +239,18 @@ int xp_tsf_untokenize(const void* tokens_bf16, void* x, int32_t x_dtype, int32_t
  * (0 or 1/keep_prob of the row's sample/group).  out may alias x. */
 int xp_rowscale_bf16(const void* x, const float* scale, const void* residual, void* out, int64_t rows, int32_t C,
                      void* stream);
+
+/* ---- BASELINE.json config #5 helpers (LF-VILA Swin-3D, LF-VILA/src/models/video_encoder.py)
+ * xp_layernorm_wide_*: nn.LayerNorm over 1024 < C <= 4096 contiguous columns — PatchMerging.norm (4C = 2048, :281,:304).
+ * xp_gather_rows_bf16 / xp_scatter_rows_bf16: out[i, :] = src[index[i], :] (zeros for index < 0) and its inverse
+ * dst[index[i], :] = in[i, :] — the 2x2 neighbour concatenation of PatchMerging.forward (:292-301; out viewed as
+ * [n/4... , 4C]) with its odd-size zero padding, and its backward. */
+int xp_layernorm_wide_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* rstd,
+                          int64_t rows, int32_t C, float eps, void* stream);
+int xp_layernorm_wide_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                          float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream);
+int xp_gather_rows_bf16(const void* src, const int32_t* index, void* out, int64_t n_items, int32_t C, void* stream);
+int xp_scatter_rows_bf16(const void* in, const int32_t* index, void* dst, int64_t n_items, int32_t C, void* stream);
 
 /* ---- retrieval evaluation.  Replaces the numpy calls of validate() (CLIP-ViP/src/pretrain/
  * run_pretrain.py:173-176, tasks/run_video_retrieval.py:155-172) on CLIP-ViP/src/utils/metrics.py:

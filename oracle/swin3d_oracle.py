@@ -243,7 +243,7 @@ def swin3d_forward(sd, video, cfg: Swin3DCfg, drop_masks: Optional[List] = None,
             shift[0] = 0
         ws, ss = clamp_window((D, H, W), window, shift)
         Dp, Hp, Wp = -(-D // ws[0]) * ws[0], -(-H // ws[1]) * ws[1], -(-W // ws[2]) * ws[2]
-        mask = shift_mask(Dp, Hp, Wp, ws, ss).to(x.dtype)
+        mask = shift_mask(Dp, Hp, Wp, ws, ss).to(device=x.device, dtype=x.dtype)
         for j in range(depth):
             blk_shift = (0, 0, 0) if j % 2 == 0 else tuple(shift)
             x = block_forward(sd, f"layers.{i}.blocks.{j}.", x, cfg.num_heads[i], window, blk_shift, mask, cfg,

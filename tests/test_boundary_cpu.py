@@ -88,3 +88,19 @@ def test_timesformer_module_has_the_reference_state_dict():
     import torch
     with pytest.raises(Exception):          # no CPU path
         m(torch.zeros(1, 7, 128, 10, 16))
+
+
+def test_swin3d_module_has_the_reference_state_dict():
+    """config #5 drop-in: parameters and buffers of LF-VILA/src/models/video_encoder.py:450-548 (no kernel is called)."""
+    import torch
+    from oracle import swin3d_oracle as SO
+    from xpretrain_b200.modeling.swin3d import SwinTransformer3D
+
+    cfg = SO.Swin3DCfg()
+    m = SwinTransformer3D(patch_norm=True, local_window=8)              # the released VideoEncoder config is the default
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == SO.param_shapes(cfg)
+    sd = SO.init_state_dict(cfg, seed=0)
+    m.load_state_dict(sd, strict=True)
+    assert torch.equal(m.layers[2].blocks[0].attn.relative_position_index, SO.rel_pos_index(cfg.window_size[2]))
+    assert sum(p.numel() for p in m.parameters()) == 89_229_448

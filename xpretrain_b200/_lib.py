@@ -34,7 +34,8 @@ class XpRowMap(C.Structure):
 class XpSegAttn(C.Structure):
     _fields_ = [("n_rows", c_i64), ("ld_qkv", c_i64), ("ld_out", c_i64), ("outer_stride", c_i64), ("inner_stride", c_i64),
                 ("tok_stride", c_i64), ("heads", c_int), ("n_seq", c_int), ("seq_len", c_int), ("seg_len", c_int),
-                ("inner", c_int), ("reserved", c_int)]
+                ("inner", c_int), ("reserved", c_int), ("row_index", c_void_p), ("bias", c_void_p), ("ds_out", c_void_p),
+                ("bias_windows", c_int), ("head_dim", c_int)]
 
 
 ACT_NONE, ACT_QUICK_GELU, ACT_DQUICK_GELU, ACT_GELU_ERF, ACT_DGELU_ERF = 0, 1, 2, 3, 4
@@ -92,7 +93,13 @@ SIGNATURES = {
                                      c_void_p]),
     "xp_tsf_embed_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "xp_tsf_untokenize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "xp_sim_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_void_p]),
+    "xp_layernorm_wide_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float,
+                                      c_void_p]),
+    "xp_layernorm_wide_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                                      c_int, c_void_p]),
+    "xp_gather_rows_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "xp_scatter_rows_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "xp_sim_f32":(c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_i64, c_void_p]),
     "xp_dsl_reweight": (c_int, [c_void_p, c_int, c_int, c_i64, c_float, c_void_p, c_void_p]),
     "xp_rank_counts": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "xp_rowscale_bf16":(c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),

@@ -308,9 +308,198 @@ rowscale_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
   *reinterpret_cast<uint4*>(out + off) = pack8(v);
 }
 
+// ------------------------------------------------- LayerNorm over rows wider than 1024 columns
+// PatchMerging's LayerNorm(4C) of LF-VILA's Swin-3D reaches 2048 columns (video_encoder.py:281,304).  One CTA of 256
+// threads per row; thread t owns columns {t*8 + k*2048}.  Rows are contiguous (ld = C).  Rarely on the critical path
+// (three launches per forward), so it favours simplicity: the row is read twice (mean, then centred variance).
+constexpr int LNW_THREADS = 256;
+constexpr int LNW_MAXK = 2;            // C <= 2 * 2048
+__device__ __forceinline__ float block_sum256(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();                     // protects `red` against the previous use
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < LNW_THREADS / 32; ++w) s += red[w];
+  return s;
+}
+__global__ void __launch_bounds__(LNW_THREADS)
+ln_wide_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out, int C,
+                   float eps) {
+  __shared__ float red[LNW_THREADS / 32];
+  const long long r = blockIdx.x;
+  const __nv_bfloat16* xr = x + r * C;
+  float v[LNW_MAXK][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LNW_MAXK; ++k) {
+    const int c = threadIdx.x * 8 + k * LNW_THREADS * 8;
+    if (c < C) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + c), v[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[k][j];
+    }
+  }
+  const float mean = block_sum256(s, red) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LNW_MAXK; ++k)
+    if (threadIdx.x * 8 + k * LNW_THREADS * 8 < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q += (v[k][j] - mean) * (v[k][j] - mean);
+    }
+  const float rstd = rsqrtf(block_sum256(q, red) / C + eps);
+#pragma unroll
+  for (int k = 0; k < LNW_MAXK; ++k) {
+    const int c = threadIdx.x * 8 + k * LNW_THREADS * 8;
+    if (c < C) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean) * rstd * gamma[c + j] + beta[c + j];
+      *reinterpret_cast<uint4*>(y + r * C + c) = pack8(o);
+    }
+  }
+  if (threadIdx.x == 0) {
+    mean_out[r] = mean;
+    rstd_out[r] = rstd;
+  }
+}
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; dgamma += dy * xhat, dbeta += dy.  Each CTA walks
+// rows blockIdx.x, blockIdx.x + gridDim.x, ... keeping its column partials of dgamma / dbeta in registers.
+__global__ void __launch_bounds__(LNW_THREADS)
+ln_wide_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, __nv_bfloat16* __restrict__ dx,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
+  __shared__ float red[LNW_THREADS / 32];
+  float ag[LNW_MAXK][8] = {}, ab[LNW_MAXK][8] = {};
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float mu = mean[r], rs = rstd[r];
+    float g[LNW_MAXK][8], xh[LNW_MAXK][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LNW_MAXK; ++k) {
+      const int c = threadIdx.x * 8 + k * LNW_THREADS * 8;
+      if (c < C) {
+        float d[8], xv[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + r * C + c), d);
+        unpack8(*reinterpret_cast<const uint4*>(x + r * C + c), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[k][j] = (xv[j] - mu) * rs;
+          g[k][j] = d[j] * gamma[c + j];
+          s1 += g[k][j];
+          s2 += g[k][j] * xh[k][j];
+          ag[k][j] += d[j] * xh[k][j];
+          ab[k][j] += d[j];
+        }
+      }
+    }
+    const float m1 = block_sum256(s1, red) / C;
+    const float m2 = block_sum256(s2, red) / C;
+#pragma unroll
+    for (int k = 0; k < LNW_MAXK; ++k) {
+      const int c = threadIdx.x * 8 + k * LNW_THREADS * 8;
+      if (c < C) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[k][j] - m1 - xh[k][j] * m2);
+        *reinterpret_cast<uint4*>(dx + r * C + c) = pack8(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LNW_MAXK; ++k) {
+    const int c = threadIdx.x * 8 + k * LNW_THREADS * 8;
+    if (c < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(dgamma + c + j, ag[k][j]);
+        atomicAdd(dbeta + c + j, ab[k][j]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------- row gather / scatter by an index table
+// out[r, k*C : (k+1)*C] = src[idx[r*segs + k], :] (zeros when the index is negative): PatchMerging's 2x2 neighbour
+// concatenation with its odd-size zero padding (video_encoder.py:292-301); scatter is the exact inverse (its backward).
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ idx, __nv_bfloat16* __restrict__ out,
+                   long long n_items, int C) {
+  const int vec = C >> 3;
+  const long long gid = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (gid >= n_items * vec) return;
+  const long long item = gid / vec;
+  const int c = static_cast<int>(gid - item * vec) * 8;
+  const int s = idx[item];
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (s >= 0) v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(s) * C + c);
+  *reinterpret_cast<uint4*>(out + item * C + c) = v;
+}
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const __nv_bfloat16* __restrict__ in, const int* __restrict__ idx, __nv_bfloat16* __restrict__ dst,
+                    long long n_items, int C) {
+  const int vec = C >> 3;
+  const long long gid = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (gid >= n_items * vec) return;
+  const long long item = gid / vec;
+  const int c = static_cast<int>(gid - item * vec) * 8;
+  const int s = idx[item];
+  if (s >= 0) *reinterpret_cast<uint4*>(dst + static_cast<long long>(s) * C + c) = *reinterpret_cast<const uint4*>(in + item * C + c);
+}
+
 }  // namespace xp
 
 using namespace xp;
+
+extern "C" int xp_layernorm_wide_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* rstd,
+                                     int64_t rows, int32_t C, float eps, void* stream) {
+  XP_ENTER(x);
+  if (C % 8 || C > LNW_MAXK * LNW_THREADS * 8) return fail("xp_layernorm_wide_fwd: C must be a multiple of 8 and <= 4096");
+  if (rows <= 0) return 0;
+  ln_wide_fwd_kernel<<<static_cast<unsigned>(rows), LNW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), gamma, beta, mean, rstd, C, eps);
+  XP_CHECK_LAUNCH("ln_wide_fwd_kernel");
+  return 0;
+}
+
+extern "C" int xp_layernorm_wide_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                     void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream) {
+  XP_ENTER(dy);
+  if (C % 8 || C > LNW_MAXK * LNW_THREADS * 8) return fail("xp_layernorm_wide_bwd: C must be a multiple of 8 and <= 4096");
+  if (rows <= 0) return 0;
+  const long long cap = 2LL * sm_count();
+  ln_wide_bwd_kernel<<<static_cast<unsigned>(rows < cap ? rows : cap), LNW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), gamma, mean, rstd,
+      static_cast<__nv_bfloat16*>(dx), dgamma, dbeta, rows, C);
+  XP_CHECK_LAUNCH("ln_wide_bwd_kernel");
+  return 0;
+}
+
+extern "C" int xp_gather_rows_bf16(const void* src, const int32_t* index, void* out, int64_t n_items, int32_t C, void* stream) {
+  XP_ENTER(src);
+  if (C % 8) return fail("xp_gather_rows_bf16: C must be a multiple of 8");
+  if (n_items <= 0) return 0;
+  const long long n = n_items * (C / 8);
+  gather_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), index, static_cast<__nv_bfloat16*>(out), n_items, C);
+  XP_CHECK_LAUNCH("gather_rows_kernel");
+  return 0;
+}
+
+extern "C" int xp_scatter_rows_bf16(const void* in, const int32_t* index, void* dst, int64_t n_items, int32_t C, void* stream) {
+  XP_ENTER(in);
+  if (C % 8) return fail("xp_scatter_rows_bf16: C must be a multiple of 8");
+  if (n_items <= 0) return 0;
+  const long long n = n_items * (C / 8);
+  scatter_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), index, static_cast<__nv_bfloat16*>(dst), n_items, C);
+  XP_CHECK_LAUNCH("scatter_rows_kernel");
+  return 0;
+}
 
 extern "C" int xp_rowscale_bf16(const void* x, const float* scale, const void* residual, void* out, int64_t rows, int32_t C,
                                 void* stream) {

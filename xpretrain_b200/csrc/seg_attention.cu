@@ -30,12 +30,19 @@ constexpr int SEG_TILE_BYTES = SEG_BLK * 128;
 struct SegDev {
   long long n_rows, ld_qkv, ld_o, outer_stride, inner_stride, tok_stride;
   int H, C, n_seq, L, seg, inner;
+  // window-attention extensions (LF-VILA Swin-3D, BASELINE.json config #5)
+  const int* idx;          // [n_seq, L] token row of every sequence position (replaces the stride pattern) or nullptr
+  const float* bias;       // [bias_nw, H, L, L] additive logits bias (relative-position bias + shift mask) or nullptr
+  __nv_bfloat16* ds_out;   // dq kernel: [n_seq, H, L, L] dL/dlogits for the bias gradient, or nullptr
+  int bias_nw;             // sequence s uses bias slab s % bias_nw
+  int hd;                  // head dim 64 or 32 (32: rows are zero-padded to 64 columns in shared memory)
 };
 
 __device__ __forceinline__ long long seq_base(const SegDev& d, int s) {
   return static_cast<long long>(s / d.inner) * d.outer_stride + static_cast<long long>(s % d.inner) * d.inner_stride;
 }
 __device__ __forceinline__ int seq_len(const SegDev& d, long long base) {
+  if (d.idx != nullptr) return d.L;
   const long long fit = (d.n_rows - base + d.tok_stride - 1) / d.tok_stride;
   return static_cast<int>(fit < d.L ? fit : d.L);
 }
@@ -43,16 +50,26 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Stage sequence positions [i0, i0+64) of one 64-column head slice into a swizzled tile; positions >= len are zero.
-__device__ __forceinline__ void stage_rows(uint32_t tile, const __nv_bfloat16* __restrict__ src, long long ld, long long base,
-                                           long long tok_stride, int i0, int len) {
+// Token row of position i of sequence s.
+__device__ __forceinline__ long long tok_row(const SegDev& d, int s, long long base, int i) {
+  return d.idx != nullptr ? static_cast<long long>(d.idx[static_cast<long long>(s) * d.L + i]) : base + i * d.tok_stride;
+}
+// Stage sequence positions [i0, i0+64) of one head slice (hd columns, zero-padded to 64) into a swizzled tile;
+// positions >= len are zero.
+__device__ __forceinline__ void stage_rows(uint32_t tile, const __nv_bfloat16* __restrict__ src, long long ld, const SegDev& d,
+                                           int s, long long base, int i0, int len) {
+  const int live_chunks = d.hd >> 3;
   for (int idx = threadIdx.x; idx < SEG_BLK * 8; idx += SEG_THREADS) {
     const int r = idx >> 3, chunk = idx & 7;
     const uint32_t dst = tile_addr(tile, r, chunk);
     const int i = i0 + r;
-    if (i < len) cp_async16(dst, src + (base + i * tok_stride) * ld + chunk * 8);
+    if (i < len && chunk < live_chunks) cp_async16(dst, src + tok_row(d, s, base, i) * ld + chunk * 8);
     else st_shared_zero16(dst);
   }
+}
+// Additive logits bias of (sequence s, head h): row q, column key at bp[q * L + key].
+__device__ __forceinline__ const float* bias_slab(const SegDev& d, int s, int h) {
+  return d.bias + ((static_cast<long long>(s % d.bias_nw) * d.H + h) * d.L) * d.L;
 }
 
 // Block range [lo, hi) (in units of 64 positions) that can interact with positions [i0, i0+64) under the segment mask.
@@ -82,19 +99,19 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   const int h = blockIdx.y, s = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long base = seq_base(d, s);
-  if (base >= d.n_rows) return;
+  if (d.idx == nullptr && base >= d.n_rows) return;
   const int len = seq_len(d, base);
   const int q0 = blockIdx.x * SEG_BLK;
   if (q0 >= len) return;
   int kb_lo, kb_hi;
   partner_blocks(d, q0, len, kb_lo, kb_hi);
-  const __nv_bfloat16* qsrc = qkv + h * HD;
+  const __nv_bfloat16* qsrc = qkv + h * d.hd;
   const __nv_bfloat16* ksrc = qsrc + d.C;
   const __nv_bfloat16* vsrc = qsrc + 2 * d.C;
 
-  stage_rows(sQ, qsrc, d.ld_qkv, base, d.tok_stride, q0, len);
-  stage_rows(sK0, ksrc, d.ld_qkv, base, d.tok_stride, kb_lo * SEG_BLK, len);
-  stage_rows(sV0, vsrc, d.ld_qkv, base, d.tok_stride, kb_lo * SEG_BLK, len);
+  stage_rows(sQ, qsrc, d.ld_qkv, d, s, base, q0, len);
+  stage_rows(sK0, ksrc, d.ld_qkv, d, s, base, kb_lo * SEG_BLK, len);
+  stage_rows(sV0, vsrc, d.ld_qkv, d, s, base, kb_lo * SEG_BLK, len);
   cp_async_commit();
 
   uint32_t qa[4][4];
@@ -114,8 +131,8 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   for (int kb = kb_lo; kb < kb_hi; ++kb) {
     const int buf = (kb - kb_lo) & 1;
     if (kb + 1 < kb_hi) {
-      stage_rows(sK0 + (buf ^ 1) * SEG_TILE_BYTES, ksrc, d.ld_qkv, base, d.tok_stride, (kb + 1) * SEG_BLK, len);
-      stage_rows(sV0 + (buf ^ 1) * SEG_TILE_BYTES, vsrc, d.ld_qkv, base, d.tok_stride, (kb + 1) * SEG_BLK, len);
+      stage_rows(sK0 + (buf ^ 1) * SEG_TILE_BYTES, ksrc, d.ld_qkv, d, s, base, (kb + 1) * SEG_BLK, len);
+      stage_rows(sV0 + (buf ^ 1) * SEG_TILE_BYTES, vsrc, d.ld_qkv, d, s, base, (kb + 1) * SEG_BLK, len);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -140,12 +157,14 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       }
     }
     float mx[2] = {-INFINITY, -INFINITY};
+    const float* bp = d.bias != nullptr ? bias_slab(d, s, h) : nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = key0 + i * 8 + (lane & 3) * 2 + (e & 1);
         const int r = e >> 1;
+        if (bp != nullptr && key < len && row_lo + r * 8 < len) sc[i][e] += bp[static_cast<long long>(row_lo + r * 8) * d.L + key];
         if (key < seg_lo[r] || key >= seg_hi[r]) sc[i][e] = -INFINITY;
         mx[r] = fmaxf(mx[r], sc[i][e]);
       }
@@ -214,16 +233,16 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   for (int it = 0; it < 4; ++it) {
     const int idx = lane + it * 32;
     const int row = warp * 16 + (idx >> 3), chunk = idx & 7;
-    if (q0 + row < len) {
+    if (q0 + row < len && chunk < (d.hd >> 3)) {
       const uint4 v = *reinterpret_cast<const uint4*>(sQ_ptr + (tile_addr(sQ, row, chunk) - sQ));
-      *reinterpret_cast<uint4*>(out + (base + (q0 + row) * d.tok_stride) * d.ld_o + h * HD + chunk * 8) = v;
+      *reinterpret_cast<uint4*>(out + tok_row(d, s, base, q0 + row) * d.ld_o + h * d.hd + chunk * 8) = v;
     }
   }
   if ((lane & 3) == 0) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int q = row_lo + r * 8;
-      if (q < len) lse[static_cast<long long>(h) * d.n_rows + base + q * d.tok_stride] = m_run[r] + logf(l_run[r]);
+      if (q < len) lse[static_cast<long long>(h) * d.n_rows + tok_row(d, s, base, q)] = m_run[r] + logf(l_run[r]);
     }
   }
 }
@@ -232,18 +251,20 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
 // 8 lanes per (row, head); delta: [H, n_rows]
 __global__ void __launch_bounds__(256)
 seg_attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                      float* __restrict__ delta, long long n_rows, int H, long long ld_o) {
+                      float* __restrict__ delta, long long n_rows, int H, long long ld_o, int hd) {
   const long long gid = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   const long long item = gid >> 3;
   const int chunk = gid & 7;
-  const bool live = item < n_rows * H;
+  const bool live = item < n_rows * H && chunk < (hd >> 3);
   float dot = 0.f;
   long long row = 0;
   int h = 0;
-  if (live) {
+  if (item < n_rows * H) {
     row = item / H;
     h = static_cast<int>(item - row * H);
-    const long long off = row * ld_o + h * HD + chunk * 8;
+  }
+  if (live) {
+    const long long off = row * ld_o + h * hd + chunk * 8;
     const uint4 g = *reinterpret_cast<const uint4*>(dout + off);
     const uint4 o = *reinterpret_cast<const uint4*>(out + off);
     const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, ow[4] = {o.x, o.y, o.z, o.w};
@@ -253,16 +274,16 @@ seg_attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16
   dot += __shfl_xor_sync(0xffffffffu, dot, 1);
   dot += __shfl_xor_sync(0xffffffffu, dot, 2);
   dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-  if (live && chunk == 0) delta[static_cast<long long>(h) * n_rows + row] = dot;
+  if (item < n_rows * H && chunk == 0) delta[static_cast<long long>(h) * n_rows + row] = dot;
 }
 
 // Stage lse * log2(e) (+inf on padding, so p = exp2(s - inf) = 0) and delta of positions [i0, i0+64).
 __device__ __forceinline__ void stage_stats(float* s_lse, float* s_delta, const float* __restrict__ lse,
-                                            const float* __restrict__ delta, const SegDev& d, int h, long long base, int i0,
-                                            int len) {
+                                            const float* __restrict__ delta, const SegDev& d, int s, int h, long long base,
+                                            int i0, int len) {
   if (threadIdx.x < SEG_BLK) {
     const int i = i0 + threadIdx.x;
-    const long long at = static_cast<long long>(h) * d.n_rows + base + i * d.tok_stride;
+    const long long at = static_cast<long long>(h) * d.n_rows + (i < len ? tok_row(d, s, base, i) : 0);
     s_lse[threadIdx.x] = i < len ? lse[at] * LOG2E : INFINITY;
     s_delta[threadIdx.x] = i < len ? delta[at] : 0.f;
   }
@@ -284,21 +305,21 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   const int h = blockIdx.y, s = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long base = seq_base(d, s);
-  if (base >= d.n_rows) return;
+  if (d.idx == nullptr && base >= d.n_rows) return;
   const int len = seq_len(d, base);
   const int k0 = blockIdx.x * SEG_BLK;
   if (k0 >= len) return;
   int qb_lo, qb_hi;
   partner_blocks(d, k0, len, qb_lo, qb_hi);
-  const __nv_bfloat16* qsrc = qkv + h * HD;
-  const __nv_bfloat16* dosrc = dout + h * HD;
+  const __nv_bfloat16* qsrc = qkv + h * d.hd;
+  const __nv_bfloat16* dosrc = dout + h * d.hd;
 
-  stage_rows(sK, qsrc + d.C, d.ld_qkv, base, d.tok_stride, k0, len);
-  stage_rows(sV, qsrc + 2 * d.C, d.ld_qkv, base, d.tok_stride, k0, len);
-  stage_rows(sQ0, qsrc, d.ld_qkv, base, d.tok_stride, qb_lo * SEG_BLK, len);
-  stage_rows(sdO0, dosrc, d.ld_o, base, d.tok_stride, qb_lo * SEG_BLK, len);
+  stage_rows(sK, qsrc + d.C, d.ld_qkv, d, s, base, k0, len);
+  stage_rows(sV, qsrc + 2 * d.C, d.ld_qkv, d, s, base, k0, len);
+  stage_rows(sQ0, qsrc, d.ld_qkv, d, s, base, qb_lo * SEG_BLK, len);
+  stage_rows(sdO0, dosrc, d.ld_o, d, s, base, qb_lo * SEG_BLK, len);
   cp_async_commit();
-  stage_stats(s_lse0, s_delta0, lse, delta, d, h, base, qb_lo * SEG_BLK, len);
+  stage_stats(s_lse0, s_delta0, lse, delta, d, s, h, base, qb_lo * SEG_BLK, len);
 
   uint32_t ka[4][4], va[4][4];
   float dk[8][4], dv[8][4];
@@ -315,13 +336,14 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     seg_hi[r] = d.seg >= d.L ? len : min(len, seg_lo[r] + d.seg);
   }
 
+  const float* bp = d.bias != nullptr ? bias_slab(d, s, h) : nullptr;
   for (int qb = qb_lo; qb < qb_hi; ++qb) {
     const int buf = (qb - qb_lo) & 1;
     if (qb + 1 < qb_hi) {
-      stage_rows(sQ0 + (buf ^ 1) * SEG_TILE_BYTES, qsrc, d.ld_qkv, base, d.tok_stride, (qb + 1) * SEG_BLK, len);
-      stage_rows(sdO0 + (buf ^ 1) * SEG_TILE_BYTES, dosrc, d.ld_o, base, d.tok_stride, (qb + 1) * SEG_BLK, len);
+      stage_rows(sQ0 + (buf ^ 1) * SEG_TILE_BYTES, qsrc, d.ld_qkv, d, s, base, (qb + 1) * SEG_BLK, len);
+      stage_rows(sdO0 + (buf ^ 1) * SEG_TILE_BYTES, dosrc, d.ld_o, d, s, base, (qb + 1) * SEG_BLK, len);
       cp_async_commit();
-      stage_stats(s_lse0 + (buf ^ 1) * SEG_BLK, s_delta0 + (buf ^ 1) * SEG_BLK, lse, delta, d, h, base, (qb + 1) * SEG_BLK, len);
+      stage_stats(s_lse0 + (buf ^ 1) * SEG_BLK, s_delta0 + (buf ^ 1) * SEG_BLK, lse, delta, d, s, h, base, (qb + 1) * SEG_BLK, len);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -358,7 +380,8 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
           const int q = qbase + ql;
           const int r = e >> 1;
           const bool valid = key_ok[r] && q >= seg_lo[r] && q < seg_hi[r];
-          const float p = valid ? fast_exp2(fmaf(st[i][e], LOG2E, -s_lse[ql])) : 0.f;
+          const float sv = (bp != nullptr && valid) ? st[i][e] + bp[static_cast<long long>(q) * d.L + key_lo + r * 8] : st[i][e];
+          const float p = valid ? fast_exp2(fmaf(sv, LOG2E, -s_lse[ql])) : 0.f;
           pt[i][e] = p;
           dst[i][e] = p * (dpt[i][e] - s_delta[ql]);
         }
@@ -385,9 +408,10 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   for (int r = 0; r < 2; ++r) {
     const int key = key_lo + r * 8;
     if (key >= len) continue;
-    __nv_bfloat16* row = dqkv + (base + key * d.tok_stride) * d.ld_qkv + h * HD + (lane & 3) * 2;
+    __nv_bfloat16* row = dqkv + tok_row(d, s, base, key) * d.ld_qkv + h * d.hd + (lane & 3) * 2;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+      if (i * 8 >= d.hd) break;
       *reinterpret_cast<uint32_t*>(row + d.C + i * 8) = pack_bf16(dk[i][2 * r], dk[i][2 * r + 1]);
       *reinterpret_cast<uint32_t*>(row + 2 * d.C + i * 8) = pack_bf16(dv[i][2 * r], dv[i][2 * r + 1]);
     }
@@ -407,20 +431,20 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   const int h = blockIdx.y, s = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long base = seq_base(d, s);
-  if (base >= d.n_rows) return;
+  if (d.idx == nullptr && base >= d.n_rows) return;
   const int len = seq_len(d, base);
   const int q0 = blockIdx.x * SEG_BLK;
   if (q0 >= len) return;
   int kb_lo, kb_hi;
   partner_blocks(d, q0, len, kb_lo, kb_hi);
-  const __nv_bfloat16* qsrc = qkv + h * HD;
+  const __nv_bfloat16* qsrc = qkv + h * d.hd;
   const __nv_bfloat16* ksrc = qsrc + d.C;
   const __nv_bfloat16* vsrc = qsrc + 2 * d.C;
 
-  stage_rows(sQ, qsrc, d.ld_qkv, base, d.tok_stride, q0, len);
-  stage_rows(sdO, dout + h * HD, d.ld_o, base, d.tok_stride, q0, len);
-  stage_rows(sK0, ksrc, d.ld_qkv, base, d.tok_stride, kb_lo * SEG_BLK, len);
-  stage_rows(sV0, vsrc, d.ld_qkv, base, d.tok_stride, kb_lo * SEG_BLK, len);
+  stage_rows(sQ, qsrc, d.ld_qkv, d, s, base, q0, len);
+  stage_rows(sdO, dout + h * d.hd, d.ld_o, d, s, base, q0, len);
+  stage_rows(sK0, ksrc, d.ld_qkv, d, s, base, kb_lo * SEG_BLK, len);
+  stage_rows(sV0, vsrc, d.ld_qkv, d, s, base, kb_lo * SEG_BLK, len);
   cp_async_commit();
 
   uint32_t qa[4][4], oa[4][4];
@@ -433,18 +457,20 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int q = q_lo + r * 8;
-    const long long at = static_cast<long long>(h) * d.n_rows + base + q * d.tok_stride;
+    const long long at = static_cast<long long>(h) * d.n_rows + (q < len ? tok_row(d, s, base, q) : 0);
     lse_r[r] = q < len ? lse[at] * LOG2E : INFINITY;
     del_r[r] = q < len ? delta[at] : 0.f;
     seg_lo[r] = d.seg >= d.L ? 0 : (q / d.seg) * d.seg;
     seg_hi[r] = d.seg >= d.L ? len : min(len, seg_lo[r] + d.seg);
   }
 
+  const float* bp = d.bias != nullptr ? bias_slab(d, s, h) : nullptr;
+  __nv_bfloat16* dsp = d.ds_out != nullptr ? d.ds_out + ((static_cast<long long>(s) * d.H + h) * d.L) * d.L : nullptr;
   for (int kb = kb_lo; kb < kb_hi; ++kb) {
     const int buf = (kb - kb_lo) & 1;
     if (kb + 1 < kb_hi) {
-      stage_rows(sK0 + (buf ^ 1) * SEG_TILE_BYTES, ksrc, d.ld_qkv, base, d.tok_stride, (kb + 1) * SEG_BLK, len);
-      stage_rows(sV0 + (buf ^ 1) * SEG_TILE_BYTES, vsrc, d.ld_qkv, base, d.tok_stride, (kb + 1) * SEG_BLK, len);
+      stage_rows(sK0 + (buf ^ 1) * SEG_TILE_BYTES, ksrc, d.ld_qkv, d, s, base, (kb + 1) * SEG_BLK, len);
+      stage_rows(sV0 + (buf ^ 1) * SEG_TILE_BYTES, vsrc, d.ld_qkv, d, s, base, (kb + 1) * SEG_BLK, len);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -479,8 +505,11 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
           const int key = kbase + sub * 16 + i * 8 + (lane & 3) * 2 + (e & 1);
           const int r = e >> 1;
           const bool valid = key >= seg_lo[r] && key < seg_hi[r];
-          const float p = valid ? fast_exp2(fmaf(sc[i][e], LOG2E, -lse_r[r])) : 0.f;
+          const int q = q_lo + r * 8;
+          const float sv = (bp != nullptr && valid && q < len) ? sc[i][e] + bp[static_cast<long long>(q) * d.L + key] : sc[i][e];
+          const float p = valid ? fast_exp2(fmaf(sv, LOG2E, -lse_r[r])) : 0.f;
           ds[i][e] = p * (dp_[i][e] - del_r[r]);
+          if (dsp != nullptr && q < len && key < len) dsp[static_cast<long long>(q) * d.L + key] = __float2bfloat16(ds[i][e]);
         }
       }
       uint32_t da[4];
@@ -500,10 +529,12 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   for (int r = 0; r < 2; ++r) {
     const int q = q_lo + r * 8;
     if (q >= len) continue;
-    __nv_bfloat16* row = dqkv + (base + q * d.tok_stride) * d.ld_qkv + h * HD + (lane & 3) * 2;
+    __nv_bfloat16* row = dqkv + tok_row(d, s, base, q) * d.ld_qkv + h * d.hd + (lane & 3) * 2;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
+      if (i * 8 >= d.hd) break;
       *reinterpret_cast<uint32_t*>(row + i * 8) = pack_bf16(dq[i][2 * r] * q_scale, dq[i][2 * r + 1] * q_scale);
+    }
   }
 }
 
@@ -512,8 +543,15 @@ static int to_dev(const XpSegAttn* a, SegDev& d, const char* who) {
   if (a->heads <= 0 || a->n_rows <= 0 || a->n_seq <= 0 || a->seq_len <= 0 || a->seg_len <= 0 || a->inner <= 0 ||
       a->tok_stride <= 0)
     return fail("xp_seg_attention: heads, n_rows, n_seq, seq_len, seg_len, inner and tok_stride must be positive");
+  d.hd = a->head_dim == 0 ? HD : a->head_dim;
+  if (d.hd != 64 && d.hd != 32) return fail("xp_seg_attention: head_dim must be 64 (or 0) or 32");
   d.H = a->heads;
-  d.C = a->heads * HD;
+  d.C = a->heads * d.hd;
+  d.idx = a->row_index;
+  d.bias = a->bias;
+  d.bias_nw = a->bias_windows > 0 ? a->bias_windows : 1;
+  d.ds_out = static_cast<__nv_bfloat16*>(a->ds_out);
+  if (d.idx != nullptr && a->seg_len < a->seq_len) return fail("xp_seg_attention: row_index sequences are dense (seg_len >= seq_len)");
   if (a->ld_qkv < 3LL * d.C || a->ld_out < d.C || a->ld_qkv % 8 || a->ld_out % 8)
     return fail("xp_seg_attention: ld_qkv >= 3*heads*64, ld_out >= heads*64, both multiples of 8");
   d.n_rows = a->n_rows; d.ld_qkv = a->ld_qkv; d.ld_o = a->ld_out;
@@ -565,7 +603,7 @@ extern "C" int xp_seg_attention_bwd(const void* qkv, const void* out, const void
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long items = d.n_rows * d.H * 8;
   seg_attn_delta_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, d.n_rows, d.H, d.ld_o);
+      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, d.n_rows, d.H, d.ld_o, d.hd);
   XP_CHECK_LAUNCH("seg_attn_delta_kernel");
   seg_attn_dkv_kernel<<<SEG_GRID(d), SEG_THREADS, SEG_DKV_SMEM, st>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,

@@ -262,6 +262,27 @@ def seg_desc(n_rows: int, heads: int, ld_qkv: int, ld_out: int, *, n_seq: int, s
     return d
 
 
+def window_desc(n_rows: int, heads: int, head_dim: int, ld_qkv: int, ld_out: int, row_index: torch.Tensor,
+                bias: Optional[torch.Tensor], ds_out: Optional[torch.Tensor] = None) -> XpSegAttn:
+    """Window attention of LF-VILA's Swin-3D (video_encoder.py:135-164,214-243): row_index int32 [n_windows, L] gives the token
+    row of every window position; bias fp32 [nW, heads, L, L] is the relative-position bias (+ shift mask per window type).
+    The descriptor keeps references to the tensors (their memory must outlive the launches)."""
+    n_win, L = row_index.shape
+    assert row_index.dtype == torch.int32 and row_index.is_contiguous()
+    d = seg_desc(n_rows, heads, ld_qkv, ld_out, n_seq=n_win, seq_len=L, seg_len=L, inner=1, outer_stride=0, inner_stride=0,
+                 tok_stride=1)
+    d.row_index = _p(row_index)
+    d.head_dim = head_dim
+    if bias is not None:
+        assert bias.dtype == f32 and bias.is_contiguous() and bias.shape[1:] == (heads, L, L)
+        d.bias, d.bias_windows = _p(bias), bias.shape[0]
+    if ds_out is not None:
+        assert ds_out.dtype == bf16 and ds_out.is_contiguous() and ds_out.shape == (n_win, heads, L, L)
+        d.ds_out = _p(ds_out)
+    d._keep = (row_index, bias, ds_out)
+    return d
+
+
 def temporal_desc(n_rows: int, T: int, heads: int, ld_qkv: int, ld_out: int) -> XpSegAttn:
     """'(b h w) t m' groups of timesformer.py:210: T consecutive rows each; 64 // T groups share one CTA tile."""
     G = max(1, 64 // T)
@@ -294,6 +315,38 @@ def rowscale(x, scale, out, residual=None):
     rows, C_ = x.shape
     assert scale.dtype == f32 and scale.numel() == rows and x.is_contiguous() and out.is_contiguous()
     check(lib().xp_rowscale_bf16(_p(x), _p(scale), _p(residual), _p(out), rows, C_, _stream()), "xp_rowscale_bf16")
+
+
+def layernorm_any_fwd(x, y, gamma, beta, mean, rstd, rows: int, C_: int, eps: float):
+    """LayerNorm over contiguous [rows, C] (the wide kernel above 1024 columns)."""
+    if C_ <= 1024:
+        m = rowmap(C_)
+        layernorm_fwd(x, m, y, m, gamma, beta, mean, rstd, rows, C_, eps)
+    else:
+        check(lib().xp_layernorm_wide_fwd(_p(x), _p(y), _p(gamma), _p(beta), _p(mean), _p(rstd), rows, C_, eps, _stream()),
+              "xp_layernorm_wide_fwd")
+
+
+def layernorm_any_bwd(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows: int, C_: int):
+    if C_ <= 1024:
+        m = rowmap(C_)
+        layernorm_bwd(dy, m, x, m, gamma, mean, rstd, dres, m if dres is not None else None, dx, m, dgamma, dbeta, rows, C_)
+    else:
+        assert dres is None
+        check(lib().xp_layernorm_wide_bwd(_p(dy), _p(x), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dgamma), _p(dbeta), rows,
+                                          C_, _stream()), "xp_layernorm_wide_bwd")
+
+
+def gather_rows(src, index, out, C_: int):
+    """out.view(-1, C)[i] = src[index[i]] (zeros for index < 0); index int32."""
+    assert index.dtype == torch.int32 and index.is_contiguous() and out.numel() == index.numel() * C_
+    check(lib().xp_gather_rows_bf16(_p(src), _p(index), _p(out), index.numel(), C_, _stream()), "xp_gather_rows_bf16")
+
+
+def scatter_rows(inp, index, dst, C_: int):
+    """dst[index[i]] = inp.view(-1, C)[i] for index >= 0."""
+    assert index.dtype == torch.int32 and index.is_contiguous() and inp.numel() == index.numel() * C_
+    check(lib().xp_scatter_rows_bf16(_p(inp), _p(index), _p(dst), index.numel(), C_, _stream()), "xp_scatter_rows_bf16")
 
 
 def tsf_untokenize(tokens, x, B, T, C_, HW):
