@@ -111,7 +111,9 @@ def run_case(ve, name, cfg, B, D, H, W, weight_seed, data_seed, train_rate=None,
     torch.save({"cfg": vars(cfg), "B": B, "D": D, "H": H, "W": W, "weight_seed": weight_seed, "data_seed": data_seed,
                 "train_rate": train_rate, "torch_seed": torch_seed, "masks": masks, "out": out.detach().clone(),
                 "loss": loss.detach(), "stage_rows": [s.flatten(0, 3)[:4].detach().clone() for s in stages],
-                "grads": {n: (ref_grads[n][:8].clone() if ref_grads[n].dim() >= 2 else ref_grads[n].clone()) for n in keep},
+                # first 8 rows of the weight matrices; bias tables (small, and only sparsely touched by clamped windows) and vectors whole
+                "grads": {n: (ref_grads[n][:8].clone() if ref_grads[n].dim() >= 2 and "bias_table" not in n
+                              else ref_grads[n].clone()) for n in keep},
                 "grad_norms": {n: float(ref_grads[n].norm()) for n in keep}},
                os.path.join(HERE, f"{name}.pt"))
 

@@ -153,7 +153,7 @@ def test_module_matches_reference_golden(dev, golden_dir, name):
     for n, ref in gold["grads"].items():
         got = params[n].grad
         assert got is not None, n
-        got = (got[:8] if ref.dim() >= 2 else got).cpu()
+        got = (got if ref.shape == got.shape else got[:8]).cpu()
         c = _cos(got, ref)
         print(f"  grad {n}: cos {c:.5f}")
         assert c > 0.985, (n, c)
