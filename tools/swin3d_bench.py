@@ -65,6 +65,30 @@ def main():
             (out.float() * w_out).sum().backward()
 
         ms = timed(ours, 5, 2)
+        ms_graph, graph_note = None, None
+        if "--graph" in sys.argv:
+            # the 24 blocks issue ~1300 small launches per step: replay them from CUDA graphs (torch.cuda.make_graphed_callables
+            # captures this module's forward and backward, all launched on the capture stream through the C ABI)
+            class First(torch.nn.Module):
+                def __init__(self, m):
+                    super().__init__()
+                    self.m = m
+
+                def forward(self, v):
+                    return self.m(v)[0]
+            try:
+                gm = torch.cuda.make_graphed_callables(First(model), (video,), num_warmup_iters=3, allow_unused_input=True)
+
+                def graphed():
+                    for p in model.parameters():
+                        p.grad = None
+                    (gm(video) * w_out).sum().backward()
+                ref_out = model(video)[0].detach()
+                got = gm(video).detach()
+                graph_note = f"graphed output rel diff {float((got - ref_out).norm() / ref_out.norm()):.1e}"
+                ms_graph = timed(graphed, 5, 2)
+            except Exception as exc:  # noqa: BLE001 - report, do not hide
+                graph_note = f"capture failed: {type(exc).__name__}: {str(exc)[:200]}"
         try:
             ms_e = timed(eager, 3, 1)
         except torch.OutOfMemoryError:
@@ -74,6 +98,7 @@ def main():
         print(json.dumps({"shape": [B, 3, D, H, W], "what": what, "ms_fwd_bwd": round(ms, 3),
                           "samples_per_s": round(B / ms * 1e3, 1), "tflops": round(fl / ms / 1e9, 1),
                           "frac_of_sustained_peak": round(fl / ms / 1e9 / peak, 3),
+                          "cuda_graph_ms": None if ms_graph is None else round(ms_graph, 3), "cuda_graph_note": graph_note,
                           "eager_bf16_ms": None if ms_e is None else round(ms_e, 3),
                           "speedup_vs_eager": None if ms_e is None else round(ms_e / ms, 2)}), flush=True)
 
