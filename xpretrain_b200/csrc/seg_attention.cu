@@ -88,6 +88,7 @@ __device__ __forceinline__ void partner_blocks(const SegDev& d, int i0, int len,
 
 // ================================================================================ forward
 // grid (ceil(L/64), H, n_seq)
+template <int HDIM>   // 64, or 32: half the k-steps of Q K^T / dO V^T and half the output column tiles
 __global__ void __launch_bounds__(SEG_THREADS, 4)
 seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                     const SegDev d) {
@@ -115,9 +116,10 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   cp_async_commit();
 
   uint32_t qa[4][4];
-  float o[8][4];
+  constexpr int KS = HDIM / 16, ND = HDIM / 8;
+  float o[ND][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  for (int i = 0; i < ND; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const int row_lo = q0 + warp * 16 + (lane >> 2);   // this thread's rows: row_lo, row_lo + 8
   int seg_lo[2], seg_hi[2];
@@ -149,7 +151,7 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
         uint32_t b[4];
         load_b_nk(sK, np * 16, ks, lane, b);
         mma_bf16(sc[2 * np], qa[ks], b[0], b[1]);
@@ -180,7 +182,7 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       m_run[r] = m_new[r];
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < ND; ++i) {
       o[i][0] *= corr[0]; o[i][1] *= corr[0];
       o[i][2] *= corr[1]; o[i][3] *= corr[1];
     }
@@ -202,7 +204,7 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       pa[2] = pack_bf16(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
       pa[3] = pack_bf16(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
+      for (int dp = 0; dp < KS; ++dp) {
         uint32_t b[4];
         load_b_kn(sV, kk * 16, dp, lane, b);
         mma_bf16(o[2 * dp], pa, b[0], b[1]);
@@ -220,7 +222,7 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   const float inv[2] = {l_run[0] > 0.f ? 1.f / l_run[0] : 0.f, l_run[1] > 0.f ? 1.f / l_run[1] : 0.f};
   // normalise, stage through this warp's (dead) Q rows, store 128-byte rows
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < ND; ++i) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int row = warp * 16 + (lane >> 2) + r * 8;
@@ -292,6 +294,7 @@ __device__ __forceinline__ void stage_stats(float* s_lse, float* s_delta, const 
 // ================================================================================ backward: dK, dV
 // grid (ceil(L/64) key blocks, H, n_seq); each warp keeps 16 keys' K, V fragments and dK, dV accumulators in registers
 // and streams the query blocks (Q, dO, lse, delta) through shared memory.
+template <int HDIM>
 __global__ void __launch_bounds__(SEG_THREADS, 3)
 seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
@@ -322,9 +325,10 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   stage_stats(s_lse0, s_delta0, lse, delta, d, s, h, base, qb_lo * SEG_BLK, len);
 
   uint32_t ka[4][4], va[4][4];
-  float dk[8][4], dv[8][4];
+  constexpr int KS = HDIM / 16, ND = HDIM / 8;
+  float dk[ND][4], dv[ND][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  for (int i = 0; i < ND; ++i) dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
   const int key_lo = k0 + warp * 16 + (lane >> 2);
   int seg_lo[2], seg_hi[2];
   bool key_ok[2];
@@ -362,7 +366,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
       if (qbase + sub * 16 >= len) break;
       float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
         uint32_t bq[4], bo[4];
         load_b_nk(sQ, sub * 16, ks, lane, bq);
         load_b_nk(sdO, sub * 16, ks, lane, bo);
@@ -392,7 +396,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
       da[0] = pack_bf16(dst[0][0], dst[0][1]); da[1] = pack_bf16(dst[0][2], dst[0][3]);
       da[2] = pack_bf16(dst[1][0], dst[1][1]); da[3] = pack_bf16(dst[1][2], dst[1][3]);
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
+      for (int dp = 0; dp < KS; ++dp) {
         uint32_t bo[4], bq[4];
         load_b_kn(sdO, sub * 16, dp, lane, bo);
         load_b_kn(sQ, sub * 16, dp, lane, bq);
@@ -410,8 +414,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     if (key >= len) continue;
     __nv_bfloat16* row = dqkv + tok_row(d, s, base, key) * d.ld_qkv + h * d.hd + (lane & 3) * 2;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i * 8 >= d.hd) break;
+    for (int i = 0; i < ND; ++i) {
       *reinterpret_cast<uint32_t*>(row + d.C + i * 8) = pack_bf16(dk[i][2 * r], dk[i][2 * r + 1]);
       *reinterpret_cast<uint32_t*>(row + 2 * d.C + i * 8) = pack_bf16(dv[i][2 * r], dv[i][2 * r + 1]);
     }
@@ -420,6 +423,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 
 // ================================================================================ backward: dQ
 // grid (ceil(L/64) query blocks, H, n_seq); Q, dO fragments + dQ accumulators in registers, K/V blocks streamed.
+template <int HDIM>
 __global__ void __launch_bounds__(SEG_THREADS, 4)
 seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
@@ -448,9 +452,10 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   cp_async_commit();
 
   uint32_t qa[4][4], oa[4][4];
-  float dq[8][4];
+  constexpr int KS = HDIM / 16, ND = HDIM / 8;
+  float dq[ND][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  for (int i = 0; i < ND; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
   const int q_lo = q0 + warp * 16 + (lane >> 2);
   float lse_r[2], del_r[2];
   int seg_lo[2], seg_hi[2];
@@ -488,7 +493,7 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       if (kbase + sub * 16 >= len) break;
       float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp_[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
         uint32_t bk[4], bv[4];
         load_b_nk(sK, sub * 16, ks, lane, bk);
         load_b_nk(sV, sub * 16, ks, lane, bv);
@@ -516,7 +521,7 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       da[0] = pack_bf16(ds[0][0], ds[0][1]); da[1] = pack_bf16(ds[0][2], ds[0][3]);
       da[2] = pack_bf16(ds[1][0], ds[1][1]); da[3] = pack_bf16(ds[1][2], ds[1][3]);
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
+      for (int dp = 0; dp < KS; ++dp) {
         uint32_t bk[4];
         load_b_kn(sK, sub * 16, dp, lane, bk);
         mma_bf16(dq[2 * dp], da, bk[0], bk[1]);
@@ -531,8 +536,7 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     if (q >= len) continue;
     __nv_bfloat16* row = dqkv + tok_row(d, s, base, q) * d.ld_qkv + h * d.hd + (lane & 3) * 2;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i * 8 >= d.hd) break;
+    for (int i = 0; i < ND; ++i) {
       *reinterpret_cast<uint32_t*>(row + i * 8) = pack_bf16(dq[i][2 * r] * q_scale, dq[i][2 * r + 1] * q_scale);
     }
   }
@@ -579,11 +583,16 @@ extern "C" int xp_seg_attention_fwd(const void* qkv, void* out, float* lse, cons
   if (d.n_seq > 65535) return fail("xp_seg_attention_fwd: n_seq > 65535 (split the call)");
   static bool attr = false;
   if (!attr) {
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_FWD_SMEM));
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_FWD_SMEM));
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_FWD_SMEM));
     attr = true;
   }
-  seg_attn_fwd_kernel<<<SEG_GRID(d), SEG_THREADS, SEG_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, d);
+  if (d.hd == 64)
+    seg_attn_fwd_kernel<64><<<SEG_GRID(d), SEG_THREADS, SEG_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, d);
+  else
+    seg_attn_fwd_kernel<32><<<SEG_GRID(d), SEG_THREADS, SEG_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, d);
   XP_CHECK_LAUNCH("seg_attn_fwd_kernel");
   return 0;
 }
@@ -596,8 +605,10 @@ extern "C" int xp_seg_attention_bwd(const void* qkv, const void* out, const void
   if (d.n_seq > 65535) return fail("xp_seg_attention_bwd: n_seq > 65535 (split the call)");
   static bool attr = false;
   if (!attr) {
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DKV_SMEM));
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DQ_SMEM));
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DKV_SMEM));
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DQ_SMEM));
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DKV_SMEM));
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dq_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DQ_SMEM));
     attr = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -605,13 +616,14 @@ extern "C" int xp_seg_attention_bwd(const void* qkv, const void* out, const void
   seg_attn_delta_kernel<<<static_cast<unsigned>((items + 255) / 256), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, d.n_rows, d.H, d.ld_o, d.hd);
   XP_CHECK_LAUNCH("seg_attn_delta_kernel");
-  seg_attn_dkv_kernel<<<SEG_GRID(d), SEG_THREADS, SEG_DKV_SMEM, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-      static_cast<__nv_bfloat16*>(dqkv), d);
+  const __nv_bfloat16* qp = static_cast<const __nv_bfloat16*>(qkv);
+  const __nv_bfloat16* dop = static_cast<const __nv_bfloat16*>(dout);
+  __nv_bfloat16* dqp = static_cast<__nv_bfloat16*>(dqkv);
+  if (d.hd == 64) seg_attn_dkv_kernel<64><<<SEG_GRID(d), SEG_THREADS, SEG_DKV_SMEM, st>>>(qp, dop, lse, delta, dqp, d);
+  else seg_attn_dkv_kernel<32><<<SEG_GRID(d), SEG_THREADS, SEG_DKV_SMEM, st>>>(qp, dop, lse, delta, dqp, d);
   XP_CHECK_LAUNCH("seg_attn_dkv_kernel");
-  seg_attn_dq_kernel<<<SEG_GRID(d), SEG_THREADS, SEG_DQ_SMEM, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), lse, delta,
-      static_cast<__nv_bfloat16*>(dqkv), d, q_scale);
+  if (d.hd == 64) seg_attn_dq_kernel<64><<<SEG_GRID(d), SEG_THREADS, SEG_DQ_SMEM, st>>>(qp, dop, lse, delta, dqp, d, q_scale);
+  else seg_attn_dq_kernel<32><<<SEG_GRID(d), SEG_THREADS, SEG_DQ_SMEM, st>>>(qp, dop, lse, delta, dqp, d, q_scale);
   XP_CHECK_LAUNCH("seg_attn_dq_kernel");
   return 0;
 }
