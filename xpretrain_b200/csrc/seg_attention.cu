@@ -88,7 +88,7 @@ __device__ __forceinline__ void partner_blocks(const SegDev& d, int i0, int len,
 
 // ================================================================================ forward
 // grid (ceil(L/64), H, n_seq)
-template <int HDIM>   // 64, or 32: half the k-steps of Q K^T / dO V^T and half the output column tiles
+template <int HDIM, bool BIAS>   // HDIM 64, or 32: half the k-steps and output column tiles; BIAS: additive logits slab
 __global__ void __launch_bounds__(SEG_THREADS, 4)
 seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                     const SegDev d) {
@@ -159,14 +159,14 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       }
     }
     float mx[2] = {-INFINITY, -INFINITY};
-    const float* bp = d.bias != nullptr ? bias_slab(d, s, h) : nullptr;
+    const float* bp = BIAS ? bias_slab(d, s, h) : nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = key0 + i * 8 + (lane & 3) * 2 + (e & 1);
         const int r = e >> 1;
-        if (bp != nullptr && key < len && row_lo + r * 8 < len) sc[i][e] += bp[static_cast<long long>(row_lo + r * 8) * d.L + key];
+        if (BIAS && key < len && row_lo + r * 8 < len) sc[i][e] += bp[static_cast<long long>(row_lo + r * 8) * d.L + key];
         if (key < seg_lo[r] || key >= seg_hi[r]) sc[i][e] = -INFINITY;
         mx[r] = fmaxf(mx[r], sc[i][e]);
       }
@@ -294,7 +294,7 @@ __device__ __forceinline__ void stage_stats(float* s_lse, float* s_delta, const 
 // ================================================================================ backward: dK, dV
 // grid (ceil(L/64) key blocks, H, n_seq); each warp keeps 16 keys' K, V fragments and dK, dV accumulators in registers
 // and streams the query blocks (Q, dO, lse, delta) through shared memory.
-template <int HDIM>
+template <int HDIM, bool BIAS>
 __global__ void __launch_bounds__(SEG_THREADS, 3)
 seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
@@ -340,7 +340,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     seg_hi[r] = d.seg >= d.L ? len : min(len, seg_lo[r] + d.seg);
   }
 
-  const float* bp = d.bias != nullptr ? bias_slab(d, s, h) : nullptr;
+  const float* bp = BIAS ? bias_slab(d, s, h) : nullptr;
   for (int qb = qb_lo; qb < qb_hi; ++qb) {
     const int buf = (qb - qb_lo) & 1;
     if (qb + 1 < qb_hi) {
@@ -384,7 +384,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
           const int q = qbase + ql;
           const int r = e >> 1;
           const bool valid = key_ok[r] && q >= seg_lo[r] && q < seg_hi[r];
-          const float sv = (bp != nullptr && valid) ? st[i][e] + bp[static_cast<long long>(q) * d.L + key_lo + r * 8] : st[i][e];
+          const float sv = (BIAS && valid) ? st[i][e] + bp[static_cast<long long>(q) * d.L + key_lo + r * 8] : st[i][e];
           const float p = valid ? fast_exp2(fmaf(sv, LOG2E, -s_lse[ql])) : 0.f;
           pt[i][e] = p;
           dst[i][e] = p * (dpt[i][e] - s_delta[ql]);
@@ -423,7 +423,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 
 // ================================================================================ backward: dQ
 // grid (ceil(L/64) query blocks, H, n_seq); Q, dO fragments + dQ accumulators in registers, K/V blocks streamed.
-template <int HDIM>
+template <int HDIM, bool BIAS>
 __global__ void __launch_bounds__(SEG_THREADS, 4)
 seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
@@ -469,7 +469,7 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     seg_hi[r] = d.seg >= d.L ? len : min(len, seg_lo[r] + d.seg);
   }
 
-  const float* bp = d.bias != nullptr ? bias_slab(d, s, h) : nullptr;
+  const float* bp = BIAS ? bias_slab(d, s, h) : nullptr;
   __nv_bfloat16* dsp = d.ds_out != nullptr ? d.ds_out + ((static_cast<long long>(s) * d.H + h) * d.L) * d.L : nullptr;
   for (int kb = kb_lo; kb < kb_hi; ++kb) {
     const int buf = (kb - kb_lo) & 1;
@@ -511,10 +511,10 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
           const int r = e >> 1;
           const bool valid = key >= seg_lo[r] && key < seg_hi[r];
           const int q = q_lo + r * 8;
-          const float sv = (bp != nullptr && valid && q < len) ? sc[i][e] + bp[static_cast<long long>(q) * d.L + key] : sc[i][e];
+          const float sv = (BIAS && valid && q < len) ? sc[i][e] + bp[static_cast<long long>(q) * d.L + key] : sc[i][e];
           const float p = valid ? fast_exp2(fmaf(sv, LOG2E, -lse_r[r])) : 0.f;
           ds[i][e] = p * (dp_[i][e] - del_r[r]);
-          if (dsp != nullptr && q < len && key < len) dsp[static_cast<long long>(q) * d.L + key] = __float2bfloat16(ds[i][e]);
+          if (BIAS && dsp != nullptr && q < len && key < len) dsp[static_cast<long long>(q) * d.L + key] = __float2bfloat16(ds[i][e]);
         }
       }
       uint32_t da[4];
@@ -583,16 +583,18 @@ extern "C" int xp_seg_attention_fwd(const void* qkv, void* out, float* lse, cons
   if (d.n_seq > 65535) return fail("xp_seg_attention_fwd: n_seq > 65535 (split the call)");
   static bool attr = false;
   if (!attr) {
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_FWD_SMEM));
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_FWD_SMEM));
+#define SEG_FOR_VARIANTS(X) X(64, false) X(64, true) X(32, false) X(32, true)
+#define SEG_ATTR_FWD(H, B) \
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_fwd_kernel<H, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_FWD_SMEM));
+    SEG_FOR_VARIANTS(SEG_ATTR_FWD)
     attr = true;
   }
-  if (d.hd == 64)
-    seg_attn_fwd_kernel<64><<<SEG_GRID(d), SEG_THREADS, SEG_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(
+  const bool with_bias = d.bias != nullptr;
+#define SEG_LAUNCH_FWD(H, B)                                                                                       \
+  if (d.hd == H && with_bias == B)                                                                                 \
+    seg_attn_fwd_kernel<H, B><<<SEG_GRID(d), SEG_THREADS, SEG_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(      \
         static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, d);
-  else
-    seg_attn_fwd_kernel<32><<<SEG_GRID(d), SEG_THREADS, SEG_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, d);
+  SEG_FOR_VARIANTS(SEG_LAUNCH_FWD)
   XP_CHECK_LAUNCH("seg_attn_fwd_kernel");
   return 0;
 }
@@ -605,10 +607,10 @@ extern "C" int xp_seg_attention_bwd(const void* qkv, const void* out, const void
   if (d.n_seq > 65535) return fail("xp_seg_attention_bwd: n_seq > 65535 (split the call)");
   static bool attr = false;
   if (!attr) {
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dkv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DKV_SMEM));
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dq_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DQ_SMEM));
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dkv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DKV_SMEM));
-    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dq_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DQ_SMEM));
+#define SEG_ATTR_BWD(H, B)                                                                                                  \
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dkv_kernel<H, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DKV_SMEM)); \
+    XP_CHECK_CUDA(cudaFuncSetAttribute(seg_attn_dq_kernel<H, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, SEG_DQ_SMEM));
+    SEG_FOR_VARIANTS(SEG_ATTR_BWD)
     attr = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -619,11 +621,14 @@ extern "C" int xp_seg_attention_bwd(const void* qkv, const void* out, const void
   const __nv_bfloat16* qp = static_cast<const __nv_bfloat16*>(qkv);
   const __nv_bfloat16* dop = static_cast<const __nv_bfloat16*>(dout);
   __nv_bfloat16* dqp = static_cast<__nv_bfloat16*>(dqkv);
-  if (d.hd == 64) seg_attn_dkv_kernel<64><<<SEG_GRID(d), SEG_THREADS, SEG_DKV_SMEM, st>>>(qp, dop, lse, delta, dqp, d);
-  else seg_attn_dkv_kernel<32><<<SEG_GRID(d), SEG_THREADS, SEG_DKV_SMEM, st>>>(qp, dop, lse, delta, dqp, d);
+  const bool with_bias = d.bias != nullptr;
+#define SEG_LAUNCH_DKV(H, B) \
+  if (d.hd == H && with_bias == B) seg_attn_dkv_kernel<H, B><<<SEG_GRID(d), SEG_THREADS, SEG_DKV_SMEM, st>>>(qp, dop, lse, delta, dqp, d);
+  SEG_FOR_VARIANTS(SEG_LAUNCH_DKV)
   XP_CHECK_LAUNCH("seg_attn_dkv_kernel");
-  if (d.hd == 64) seg_attn_dq_kernel<64><<<SEG_GRID(d), SEG_THREADS, SEG_DQ_SMEM, st>>>(qp, dop, lse, delta, dqp, d, q_scale);
-  else seg_attn_dq_kernel<32><<<SEG_GRID(d), SEG_THREADS, SEG_DQ_SMEM, st>>>(qp, dop, lse, delta, dqp, d, q_scale);
+#define SEG_LAUNCH_DQ(H, B) \
+  if (d.hd == H && with_bias == B) seg_attn_dq_kernel<H, B><<<SEG_GRID(d), SEG_THREADS, SEG_DQ_SMEM, st>>>(qp, dop, lse, delta, dqp, d, q_scale);
+  SEG_FOR_VARIANTS(SEG_LAUNCH_DQ)
   XP_CHECK_LAUNCH("seg_attn_dq_kernel");
   return 0;
 }
