@@ -89,7 +89,7 @@ __device__ __forceinline__ void partner_blocks(const SegDev& d, int i0, int len,
 // ================================================================================ forward
 // grid (ceil(L/64), H, n_seq)
 template <int HDIM, bool BIAS>   // HDIM 64, or 32: half the k-steps and output column tiles; BIAS: additive logits slab
-__global__ void __launch_bounds__(SEG_THREADS, 4)
+__global__ void __launch_bounds__(SEG_THREADS, HDIM == 32 ? 5 : 4)   // small windows are latency-bound: more resident CTAs
 seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                     const SegDev d) {
   extern __shared__ uint8_t smem_raw[];
@@ -295,7 +295,7 @@ __device__ __forceinline__ void stage_stats(float* s_lse, float* s_delta, const 
 // grid (ceil(L/64) key blocks, H, n_seq); each warp keeps 16 keys' K, V fragments and dK, dV accumulators in registers
 // and streams the query blocks (Q, dO, lse, delta) through shared memory.
 template <int HDIM, bool BIAS>
-__global__ void __launch_bounds__(SEG_THREADS, 3)
+__global__ void __launch_bounds__(SEG_THREADS, HDIM == 32 ? 4 : 3)
 seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                     const SegDev d) {
@@ -424,7 +424,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 // ================================================================================ backward: dQ
 // grid (ceil(L/64) query blocks, H, n_seq); Q, dO fragments + dQ accumulators in registers, K/V blocks streamed.
 template <int HDIM, bool BIAS>
-__global__ void __launch_bounds__(SEG_THREADS, 4)
+__global__ void __launch_bounds__(SEG_THREADS, HDIM == 32 ? 5 : 4)
 seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                    const SegDev d, float q_scale) {
