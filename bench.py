@@ -221,7 +221,8 @@ def run_ours(args):
         achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         roof = {"kernel": "xp::gemm_kernel (tcgen05 bf16, all launches of one step)", "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["tflops"], 4), "traffic": ncu_traffic(), "peak_source": peaks["source"],
+                "frac": round(achieved / peaks["tflops"], 4), "traffic": ncu_traffic()[0],
+                "traffic_of": ncu_traffic()[1], "peak_source": peaks["source"],
                 "launches_per_step": len(rec), "gemm_ms_per_step": round(g_ms, 3),
                 "gemm_share_of_step": round(g_ms / ms_resident, 4)}
 
@@ -309,16 +310,17 @@ def run_ours(args):
 
 
 def ncu_traffic():
-    """dram__bytes_read+write of one captured GEMM launch (profiles/r01_ncu_gemm_traffic.json names the launch and its
-    algorithmic bytes); None when no capture is committed."""
+    """(dram__bytes_read + dram__bytes_write of one captured GEMM launch, what that launch was) from
+    profiles/r01_ncu_gemm_traffic.json; (None, None) when no capture is committed."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_gemm_traffic.json")
     try:
         with open(path) as f:
             d = json.load(f)
-        return {"bytes": d["traffic_bytes"], "algorithmic_bytes": d["algorithmic_bytes"]["total"],
-                "launch": f"{d['kernel']} M={d['shape']['M']} N={d['shape']['N']} K={d['shape']['K']}"}
+        return d["traffic_bytes"], {"algorithmic_bytes": d["algorithmic_bytes"]["total"],
+                                    "launch": f"{d['kernel']} M={d['shape']['M']} N={d['shape']['N']} K={d['shape']['K']}",
+                                    "source": "profiles/r01_ncu_gemm_traffic.json (one ncu --set full capture)"}
     except (OSError, KeyError, ValueError):
-        return None
+        return None, None
 
 
 # -------------------------------------------------------------------------------- reference / CPU arm
