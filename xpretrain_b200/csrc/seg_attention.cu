@@ -146,8 +146,16 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     const int key0 = kb * SEG_BLK;
 
     float sc[8][4];
+    const float* bp = BIAS ? bias_slab(d, s, h) : nullptr;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {   // accumulators start at the additive bias: its loads overlap the Q K^T MMAs
+        const int key = key0 + i * 8 + (lane & 3) * 2 + (e & 1);
+        const int q = row_lo + (e >> 1) * 8;
+        sc[i][e] = (BIAS && key < len && q < len) ? bp[static_cast<long long>(q) * d.L + key] : 0.f;
+      }
+    }
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
 #pragma unroll
@@ -159,14 +167,12 @@ seg_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
       }
     }
     float mx[2] = {-INFINITY, -INFINITY};
-    const float* bp = BIAS ? bias_slab(d, s, h) : nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int key = key0 + i * 8 + (lane & 3) * 2 + (e & 1);
         const int r = e >> 1;
-        if (BIAS && key < len && row_lo + r * 8 < len) sc[i][e] += bp[static_cast<long long>(row_lo + r * 8) * d.L + key];
         if (key < seg_lo[r] || key >= seg_hi[r]) sc[i][e] = -INFINITY;
         mx[r] = fmaxf(mx[r], sc[i][e]);
       }
@@ -364,7 +370,16 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 #pragma unroll 1
     for (int sub = 0; sub < 4; ++sub) {
       if (qbase + sub * 16 >= len) break;
-      float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float st[2][4], dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {   // S^T accumulators start at the additive bias (loads overlap the MMAs)
+          const int q = qbase + sub * 16 + i * 8 + (lane & 3) * 2 + (e & 1);
+          const int key = key_lo + (e >> 1) * 8;
+          st[i][e] = (BIAS && q < len && key < len) ? bp[static_cast<long long>(q) * d.L + key] : 0.f;
+        }
+      }
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t bq[4], bo[4];
@@ -384,8 +399,7 @@ seg_attn_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
           const int q = qbase + ql;
           const int r = e >> 1;
           const bool valid = key_ok[r] && q >= seg_lo[r] && q < seg_hi[r];
-          const float sv = (BIAS && valid) ? st[i][e] + bp[static_cast<long long>(q) * d.L + key_lo + r * 8] : st[i][e];
-          const float p = valid ? fast_exp2(fmaf(sv, LOG2E, -s_lse[ql])) : 0.f;
+          const float p = valid ? fast_exp2(fmaf(st[i][e], LOG2E, -s_lse[ql])) : 0.f;
           pt[i][e] = p;
           dst[i][e] = p * (dpt[i][e] - s_delta[ql]);
         }
@@ -491,7 +505,16 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll 1
     for (int sub = 0; sub < 4; ++sub) {
       if (kbase + sub * 16 >= len) break;
-      float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp_[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float sc[2][4], dp_[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {   // logits accumulators start at the additive bias (loads overlap the MMAs)
+          const int key = kbase + sub * 16 + i * 8 + (lane & 3) * 2 + (e & 1);
+          const int q = q_lo + (e >> 1) * 8;
+          sc[i][e] = (BIAS && q < len && key < len) ? bp[static_cast<long long>(q) * d.L + key] : 0.f;
+        }
+      }
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t bk[4], bv[4];
@@ -511,8 +534,7 @@ seg_attn_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
           const int r = e >> 1;
           const bool valid = key >= seg_lo[r] && key < seg_hi[r];
           const int q = q_lo + r * 8;
-          const float sv = (BIAS && valid && q < len) ? sc[i][e] + bp[static_cast<long long>(q) * d.L + key] : sc[i][e];
-          const float p = valid ? fast_exp2(fmaf(sv, LOG2E, -lse_r[r])) : 0.f;
+          const float p = valid ? fast_exp2(fmaf(sc[i][e], LOG2E, -lse_r[r])) : 0.f;
           ds[i][e] = p * (dp_[i][e] - del_r[r]);
           if (BIAS && dsp != nullptr && q < len && key < len) dsp[static_cast<long long>(q) * d.L + key] = __float2bfloat16(ds[i][e]);
         }
