@@ -188,16 +188,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// bf16 pair packing WITHOUT the conversion unit.  cvt.rn.bf16x2.f32 (F2FP) issues on the XU pipe (16 lanes/clk/SM),
-// the same pipe as MUFU.TANH / MUFU.EX2 — ncu showed that pipe saturated in the GELU epilogues and the softmax.
-// Veltkamp split on the FMA pipe instead: c = x*(2^16+1); hi = c - (c - x) is x rounded to 8 significant bits
-// (round-to-nearest), whose low 16 bits are zero, so the bf16 is its high half (one PRMT per pair).
-// __fmul_rn/__fsub_rn are never contracted into FMAs.  (|x| > 5e33 would overflow c; activations never get there.)
-__device__ __forceinline__ uint32_t pack_bf16_fma(float lo, float hi) {
-  const float cl = __fmul_rn(lo, 65537.f), ch = __fmul_rn(hi, 65537.f);
-  const float rl = __fsub_rn(cl, __fsub_rn(cl, lo)), rh = __fsub_rn(ch, __fsub_rn(ch, hi));
-  return __byte_perm(__float_as_uint(rl), __float_as_uint(rh), 0x7632);
-}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
