@@ -366,6 +366,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # bounded sample: pick the pairs per step so that W + K steps end within ~4 minutes on this host (probe: one pair)
+    import torch
+    torch.set_num_threads(min(os.cpu_count() or 1, 64))
+    probe = cpu_step_fn(1)
+    t0 = time.perf_counter()
+    probe()
+    per_pair = time.perf_counter() - t0
+    del probe
+    budget = 240.0 / max(1, args.steps + args.warmup)
+    args.cpu_batch = next((b for b in (args.cpu_batch, 2, 1) if b <= args.cpu_batch and b * per_pair <= budget), 1)
     base = cpu_baseline(steps=args.steps, warmup=args.warmup, batch=args.cpu_batch)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(base["seconds_per_step"] * 1e3, 2),
