@@ -94,3 +94,21 @@ def test_swin3d_index_tables_equal_the_reference_pad_roll_partition(B, D, H, W, 
     xm = F.pad(x, (0, 0, 0, W % 2, 0, H % 2)) if (H % 2 or W % 2) else x
     want = torch.cat([xm[:, :, 0::2, 0::2], xm[:, :, 1::2, 0::2], xm[:, :, 0::2, 1::2], xm[:, :, 1::2, 1::2]], -1).reshape(-1).long() - 1
     assert (H2, W2) == ((H + 1) // 2, (W + 1) // 2) and torch.equal(midx.long(), want)
+
+
+def test_retrieval_metrics_host_part_matches_reference_semantics_with_ties():
+    """utils.metrics.metrics_from_counts (pure numpy) vs the oracle's compute_metrics on matrices with many exact ties."""
+    import numpy as np
+    from oracle import metrics_oracle as MO
+    from xpretrain_b200.utils.metrics import metrics_from_counts
+
+    rng = np.random.RandomState(0)
+    for n in (1, 2, 7, 40):
+        for levels in (3, 1000):                                 # few distinct values -> lots of ties with the diagonal
+            x = rng.randint(0, levels, size=(n, n)).astype(np.float32)
+            g, e = MO.rank_counts(x)
+            assert tuple(float(v) for v in metrics_from_counts(g, e)) == tuple(float(v) for v in MO.compute_metrics(x))
+            # and the oracle's count-based form equals the reference's sort-based definition
+            sx = np.sort(-x, axis=1)
+            ind = np.where(sx - np.diag(-x)[:, None] == 0)[1]
+            assert np.array_equal(np.sort(ind), np.sort(MO.ranks_from_counts(g, e)))

@@ -63,8 +63,14 @@ def rank_counts(sim: torch.Tensor, transpose: bool = False):
 def compute_metrics(x: torch.Tensor, transpose: bool = False):
     """metrics.py:41-53 on a device similarity matrix; compute_metrics(sim, transpose=True) == reference compute_metrics(sim.T)."""
     greater, equal = rank_counts(x, transpose)
-    g, e = greater.cpu().numpy(), equal.cpu().numpy()
-    ind = np.repeat(g, e) + (np.arange(int(e.sum())) - np.repeat(np.cumsum(e) - e, e))   # g_i, g_i+1, .., g_i+e_i-1 per row
+    return metrics_from_counts(greater.cpu().numpy(), equal.cpu().numpy())
+
+
+def metrics_from_counts(g: np.ndarray, e: np.ndarray):
+    """The O(N) host part of compute_metrics: the reference's rank list `ind` (metrics.py:42-47) is, per query,
+    g_i, g_i + 1, .., g_i + e_i - 1 (one entry per value tied with the diagonal), then recall@1/5/10, median and mean rank."""
+    g, e = np.asarray(g, dtype=np.int64), np.asarray(e, dtype=np.int64)
+    ind = np.repeat(g, e) + (np.arange(int(e.sum())) - np.repeat(np.cumsum(e) - e, e))
     r1 = float(np.sum(ind == 0)) / len(ind)
     r5 = float(np.sum(ind < 5)) / len(ind)
     r10 = float(np.sum(ind < 10)) / len(ind)
