@@ -295,6 +295,10 @@ int xp_opt_scale_grads(const XpOptTensor* table_dev, const int32_t* block_map_de
                        void* stream);
 int xp_opt_adamw_step(const XpOptTensor* table_dev, const int32_t* block_map_dev, int32_t n_blocks, const float* norm_dev,
                       float beta1, float beta2, float eps, void* stream);
+/* Multi-tensor refresh of the bf16 compute copies (replaces the reference's implicit "the module reads its own fp32
+ * parameters", CLIP_ViP.py:445-460): per row, g = fp32 source, p_bf16 = bf16 destination, or if that is null p = fp32
+ * destination (plain copy); n elements.  One launch for all weights of a tower, run on every forward. */
+int xp_cast_table(const XpOptTensor* table_dev, const int32_t* block_map_dev, int32_t n_blocks, void* stream);
 
 #ifdef __cplusplus
 }

@@ -255,6 +255,24 @@ def nce_vsc_fc_loss(vis: Tensor, txt: Tensor, img: Tensor, cap: Tensor, logit_sc
     return sum(t.mean() for t in terms)
 
 
+def run_reduced_precision(sd: Dict[str, Tensor], video: Tensor, input_ids: Tensor, attention_mask: Tensor, cfg: "ClipVipCfg",
+                          device, mode: str):
+    """Calibration arm of the parity tests: THIS restatement of the reference algorithm run in reduced precision on `device`.
+    mode 'autocast' = fp32 weights under torch.autocast(bf16) — the only way the reference itself runs in bf16 (its `.to(bf16)`
+    crashes in the mask code); mode 'pure' = every floating tensor in bf16 (what apex amp O2 does in fp16,
+    run_pretrain.py:234-236).  Returns (vis, txt, loss, {name: grad}) as fp32 CPU values."""
+    dt = torch.bfloat16 if mode == "pure" else torch.float32
+    dev = torch.device(device)
+    sdg = {k: (v.detach().to(dev, dt, copy=True).requires_grad_(True) if v.is_floating_point() else v.to(dev))
+           for k, v in sd.items()}
+    with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=(mode == "autocast")):
+        o = clip_vip_forward(sdg, video.to(dev, dt), input_ids.to(dev), attention_mask.to(dev), cfg)
+        loss = nce_learnable_temp_loss(o["vis_features"].float(), o["text_features"].float(), sdg["logit_scale"].float())
+    loss.backward()
+    grads = {k: t.grad.detach().float().cpu() for k, t in sdg.items() if t.is_floating_point() and t.grad is not None}
+    return o["vis_features"].detach().float().cpu(), o["text_features"].detach().float().cpu(), float(loss.detach()), grads
+
+
 def gather_rank_major(per_rank: list) -> Tensor:
     """hvd.allgather (run_pretrain.py:344-345) / SyncFunction.forward (LF-VILA/src/utils/dist.py:21-33):
     rank-major concatenation along dim 0."""

@@ -49,7 +49,25 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-def run_case(name, cfg, B, T, Lt, ragged, weight_seed, data_seed, with_hidden):
+# full-tensor gradients kept by the full-depth case (fp16 after a per-tensor max-normalisation; every bias / LayerNorm
+# vector of the model is kept whole in fp32 as well)
+FULL_GRAD_KEYS = (
+    "vision_model.encoder.layers.11.mlp.fc1.weight", "vision_model.encoder.layers.0.self_attn.q_proj.weight",
+    "vision_model.encoder.layers.0.self_attn.k_proj.weight", "vision_model.encoder.layers.0.self_attn.out_proj.weight",
+    "vision_model.encoder.layers.11.self_attn.out_proj.weight", "vision_model.encoder.layers.11.self_attn.v_proj.weight",
+    "vision_model.embeddings.patch_embedding.weight", "vision_model.embeddings.position_embedding.weight",
+    "text_model.encoder.layers.0.mlp.fc1.weight", "text_model.encoder.layers.11.self_attn.q_proj.weight",
+    "visual_projection.weight", "text_projection.weight",
+)
+ROW_GRAD_KEYS = {"vision_model.encoder.layers.0.mlp.fc1.weight": 512, "vision_model.encoder.layers.0.mlp.fc2.weight": 128}
+
+
+def _pack_f16(g):
+    s = float(g.abs().max().clamp_min(1e-30))
+    return {"scale": s, "data": (g / s).to(torch.float16)}
+
+
+def run_case(name, cfg, B, T, Lt, ragged, weight_seed, data_seed, with_hidden, full_grads=False):
     from src.optimization.loss import NCELearnableTempLoss
 
     sd = O.init_state_dict(cfg, seed=weight_seed)
@@ -96,6 +114,18 @@ def run_case(name, cfg, B, T, Lt, ragged, weight_seed, data_seed, with_hidden):
                                                  "visual_projection", "text_projection",
                                                  "vision_model.embeddings.position_embedding"))},
     }
+    if full_grads:
+        full = {k: _pack_f16(grads[k]) for k in FULL_GRAD_KEYS}
+        for k, n in ROW_GRAD_KEYS.items():
+            full[k + f"[:{n}]"] = _pack_f16(grads[k][:n])
+        tk = "text_model.embeddings.token_embedding.weight"
+        rows = torch.unique(ids)
+        full[tk + "[rows]"] = {"rows": rows, **_pack_f16(grads[tk][rows])}
+        rest = grads[tk].clone()
+        rest[rows] = 0
+        assert float(rest.abs().max()) == 0.0                                        # untouched rows: exactly zero
+        gold["grad_full"] = full
+        gold["grad_vectors"] = {k: g.clone() for k, g in grads.items() if g.dim() <= 1 or g.numel() <= 4096}
     if with_hidden:
         vh = out["vision_model_output"].hidden_states
         th = out["text_model_output"].hidden_states
@@ -161,6 +191,10 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     full = O.ClipVipCfg()
+    if len(sys.argv) > 1 and sys.argv[1] == "full12":      # the BENCH shape: T = 12, 12 + 12 layers, ragged text, full gradients
+        run_case("full12_b4_t12_ragged", full, B=4, T=12, Lt=32, ragged=True, weight_seed=3, data_seed=4321,
+                 with_hidden=False, full_grads=True)
+        sys.exit(0)
     # BASELINE.json configs[0]: ViT-B/16, 1 video x 4 frames, 32 tokens, batch 2, fp32 CPU (temporal interp 12 -> 4)
     run_case("cfg1_b2_t4", full, B=2, T=4, Lt=32, ragged=False, weight_seed=0, data_seed=1234, with_hidden=False)
     # reduced depth, native T=12, ragged text (EOS not last, padding mask active), hidden states kept

@@ -104,3 +104,34 @@ def test_swin3d_module_has_the_reference_state_dict():
     m.load_state_dict(sd, strict=True)
     assert torch.equal(m.layers[2].blocks[0].attn.relative_position_index, SO.rel_pos_index(cfg.window_size[2]))
     assert sum(p.numel() for p in m.parameters()) == 89_229_448
+
+
+def test_init_weights_statistics_follow_the_reference():
+    """CLIPPreTrainedModel._init_weights (CLIP_ViP.py:481-522, factor 1, initializer_range 0.02) + the ViP additions
+    (`added_cls ~ N(0,1)` :153, `temporal_embedding = 0` :166): sample std of every tensor family within 3 % of the nominal."""
+    import torch
+    from xpretrain_b200.modeling.clip_vip import CLIPModel, ClipVipConfig
+    torch.manual_seed(0)
+    cfg = ClipVipConfig()
+    m = CLIPModel(cfg)
+    def std(t): return float(t.detach().float().std())
+    def close(got, want): assert abs(got - want) < 0.03 * want, (got, want)
+    ve, te = m.vision_model.embeddings, m.text_model.embeddings
+    close(std(te.token_embedding.weight), 0.02); close(std(te.position_embedding.weight), 0.02)
+    close(std(ve.patch_embedding.weight), 0.02); close(std(ve.position_embedding.weight), 0.02)
+    assert abs(std(ve.class_embedding) - 768 ** -0.5) < 0.15 * 768 ** -0.5      # 768 samples only: wider band
+    assert abs(std(ve.added_cls) - 1.0) < 0.1                           # N(0, 1), 3 x 768 samples
+    assert float(ve.temporal_embedding.abs().max()) == 0.0
+    for tower, tc in ((m.vision_model, cfg.vision), (m.text_model, cfg.text)):
+        in_std = tc.hidden_size ** -0.5 * (2 * tc.num_hidden_layers) ** -0.5
+        for layer in (tower.encoder.layers[0], tower.encoder.layers[-1]):
+            for lin in (layer.self_attn.q_proj, layer.self_attn.k_proj, layer.self_attn.v_proj, layer.mlp.fc2):
+                close(std(lin.weight), in_std)
+            close(std(layer.self_attn.out_proj.weight), tc.hidden_size ** -0.5)
+            close(std(layer.mlp.fc1.weight), (2 * tc.hidden_size) ** -0.5)
+            for lin in (layer.self_attn.q_proj, layer.self_attn.out_proj, layer.mlp.fc1, layer.mlp.fc2):
+                assert float(lin.bias.abs().max()) == 0.0
+            for ln in (layer.layer_norm1, layer.layer_norm2):
+                assert float((ln.weight - 1).abs().max()) == 0.0 and float(ln.bias.abs().max()) == 0.0
+    close(std(m.visual_projection.weight), 768 ** -0.5); close(std(m.text_projection.weight), 512 ** -0.5)
+    assert abs(float(m.logit_scale) - 4.60) < 1e-6

@@ -1,0 +1,143 @@
+"""B200: the rest of the drop-in boundary (SURVEY.md §8b / VERDICT r1 items a12, a13, b):
+`forward_video` / `forward_text` / `get_*_features(if_norm)` (VidCLIP.py:83-90, CLIP_ViP.py:992-1085),
+`freeze_text_encoder` (VidCLIP.py:92-103), and the contract that a weight written IN PLACE through `p.data` — the idiom
+of the reference's own AdamW (CLIP-ViP/src/optimization/adamw.py:89,101), which autograd's version counter does not see —
+is what the next forward computes with."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+    return torch.device("cuda", 0)
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+
+
+def _small(dev, seed=3, layers=2):
+    from oracle import clipvip_oracle as O
+    from xpretrain_b200.modeling import VidCLIP
+    from xpretrain_b200.modeling.clip_vip import ClipVipConfig, TowerConfig
+    cfg = O.ClipVipCfg(vision=O.TowerCfg(768, 12, layers, 3072), text=O.TowerCfg(512, 8, layers, 2048))
+    sd = O.init_state_dict(cfg, seed=seed)
+    add = SimpleNamespace(type="ViP", temporal_size=12, if_use_temporal_embed=1, logit_scale_init_value=4.6, add_cls_num=3)
+    mc = ClipVipConfig(vision=TowerConfig(768, 12, layers, 3072), text=TowerConfig(512, 8, layers, 2048))
+    model = VidCLIP(SimpleNamespace(clip_config=mc, clip_weights="", clip_vision_additional_config=add))
+    model.clipmodel.load_state_dict(sd, strict=False)
+    return O, cfg, sd, model.to(dev)
+
+
+def test_single_tower_entry_points_against_oracle(dev):
+    O, cfg, sd, model = _small(dev)
+    video, ids, mask = O.synthetic_batch(3, 2, 16, cfg, seed=8, ragged_text=True)
+    want = O.clip_vip_forward(sd, video, ids, mask, cfg)
+    vproj, _ = O.vision_tower(sd, video, cfg), None
+    with torch.no_grad():
+        fv = model.forward_video(video.to(dev))
+        ft = model.forward_text(ids.to(dev), mask.to(dev))
+        gi_n = model.clipmodel.get_image_features(pixel_values=video.to(dev), if_norm=True)
+        gi_raw = model.clipmodel.get_image_features(pixel_values=video.to(dev))              # if_norm=None -> un-normalised
+        gt_raw = model.clipmodel.get_text_features(input_ids=ids.to(dev), attention_mask=mask.to(dev), if_norm=False)
+        both = model(video=video.to(dev), text_input_ids=ids.to(dev), text_input_mask=mask.to(dev))
+    assert torch.equal(fv, both["vis_features"]) and torch.equal(ft, both["text_features"]) and torch.equal(gi_n, fv)
+    assert _rel(fv.cpu(), want["vis_features"]) < 1e-2 and _rel(ft.cpu(), want["text_features"]) < 1e-2
+    # un-normalised projections (CLIP_ViP.py:1039-1041, 1083-1085): the oracle towers return them before l2_normalize
+    vis_raw = O.vision_tower(sd, video, cfg)
+    txt_raw = O.text_tower(sd, ids, mask, cfg)
+    assert _rel(gi_raw.cpu(), vis_raw) < 1e-2 and _rel(gt_raw.cpu(), txt_raw) < 1e-2
+    assert float((gi_raw.norm(dim=-1) - 1).abs().min()) > 1e-3          # really not normalised
+    assert _rel(torch.nn.functional.normalize(gi_raw, dim=-1).cpu(), fv.cpu()) < 1e-5
+
+
+def test_freeze_text_encoder(dev):
+    from xpretrain_b200.optimization.loss import NCELearnableTempLoss
+    O, cfg, sd, model = _small(dev, seed=4)
+    video, ids, mask = O.synthetic_batch(4, 2, 16, cfg, seed=9)
+    video, ids, mask = video.to(dev), ids.to(dev), mask.to(dev)
+
+    def run():
+        model.zero_grad(set_to_none=True)
+        out = model(video=video, text_input_ids=ids, text_input_mask=mask)
+        loss = NCELearnableTempLoss()(out["vis_features"], out["text_features"], model.clipmodel.logit_scale)
+        loss.backward()
+        return float(loss), {n: (p.grad.clone() if p.grad is not None else None) for n, p in model.clipmodel.named_parameters()}
+
+    l0, g0 = run()
+    model.freeze_text_encoder(freeze_text_proj=False)
+    l1, g1 = run()
+    assert l0 == l1
+    for n, g in g1.items():
+        if n.startswith("text_model."):
+            assert g is None, n
+        else:
+            assert g is not None and torch.equal(g, g0[n]), n            # vision / projections / logit_scale intact
+    model.freeze_text_encoder(freeze_text_proj=True)
+    _, g2 = run()
+    assert g2["text_projection.weight"] is None and all(g is None for n, g in g2.items() if n.startswith("text_model."))
+    assert torch.equal(g2["visual_projection.weight"], g0["visual_projection.weight"])
+
+
+def test_inplace_data_updates_of_the_reference_adamw_reach_the_next_forward(dev):
+    """the driver keeps the reference optimizer.  Its step writes `p.data.addcdiv_` / `p.data.add_`
+    (adamw.py:89,101), which leaves `p._version` unchanged — the next forward must still see the new weights."""
+    from oracle import adamw_oracle as A
+    from xpretrain_b200.optimization.loss import NCELearnableTempLoss
+    O, cfg, sd, model = _small(dev, seed=6, layers=1)
+    video, ids, mask = O.synthetic_batch(2, 2, 16, cfg, seed=10)
+    dvideo, dids, dmask = video.to(dev), ids.to(dev), mask.to(dev)
+    out0 = model(video=dvideo, text_input_ids=dids, text_input_mask=dmask)
+    NCELearnableTempLoss()(out0["vis_features"], out0["text_features"], model.clipmodel.logit_scale).backward()
+    versions = {n: p._version for n, p in model.clipmodel.named_parameters()}
+    for n, p in model.clipmodel.named_parameters():                      # the reference AdamW step, restated (oracle/adamw_oracle.py)
+        m, v = torch.zeros_like(p.data), torch.zeros_like(p.data)
+        A.adamw_step(p.data, p.grad.data, m, v, step=1, lr=2e-2, weight_decay=0.0 if "bias" in n else 0.2)
+    assert all(p._version == versions[n] for n, p in model.clipmodel.named_parameters())   # autograd did not notice
+    with torch.no_grad():
+        out1 = model(video=dvideo, text_input_ids=dids, text_input_mask=dmask)
+    assert _rel(out1["vis_features"], out0["vis_features"].detach()) > 5e-2                 # the forward moved ...
+    new_sd = {k: v.detach().cpu() for k, v in model.clipmodel.state_dict().items()}
+    want = O.clip_vip_forward(new_sd, video, ids, mask, cfg)                                 # ... to where the fp32 oracle goes
+    assert _rel(out1["vis_features"].cpu(), want["vis_features"]) < 1e-2
+    assert _rel(out1["text_features"].cpu(), want["text_features"]) < 1e-2
+    # same contract for load_state_dict and overload_logit_scale-style fills
+    model.clipmodel.load_state_dict(sd, strict=False)
+    with torch.no_grad():
+        out2 = model(video=dvideo, text_input_ids=dids, text_input_mask=dmask)
+    assert torch.equal(out2["vis_features"], out0["vis_features"].detach())
+
+
+def test_evaluation_forward_keeps_no_activations(dev):
+    """under no_grad the autograd.Function must not save the per-layer activations."""
+    O, cfg, sd, model = _small(dev, seed=7, layers=2)
+    video, ids, mask = O.synthetic_batch(4, 4, 16, cfg, seed=11)
+    video, ids, mask = video.to(dev), ids.to(dev), mask.to(dev)
+    def peak(grad):
+        torch.cuda.synchronize(); torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        with torch.set_grad_enabled(grad):
+            out = model(video=video, text_input_ids=ids, text_input_mask=mask)
+        torch.cuda.synchronize()
+        return torch.cuda.max_memory_allocated() - base, out
+    p_eval, _ = peak(False)
+    p_train, _ = peak(True)
+    print(f"peak forward memory: eval {p_eval / 2**20:.1f} MiB, train {p_train / 2**20:.1f} MiB")
+    assert p_eval < 0.6 * p_train
+
+
+def test_text_length_and_token_id_validation(dev):
+    O, cfg, sd, model = _small(dev, seed=7, layers=1)
+    ids = torch.full((2, 78), 5, dtype=torch.int64, device=dev)
+    with pytest.raises(ValueError):
+        model.forward_text(ids, torch.ones_like(ids))
+    model.clipmodel.validate_ids = True
+    bad = torch.full((2, 8), 49408, dtype=torch.int64, device=dev)
+    with pytest.raises(IndexError):
+        model.forward_text(bad, torch.ones_like(bad))

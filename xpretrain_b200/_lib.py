@@ -106,6 +106,7 @@ SIGNATURES = {
     "xp_opt_chunk_elems": (c_int, []),
     "xp_opt_grad_norm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "xp_opt_scale_grads": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "xp_cast_table": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "xp_opt_adamw_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_float, c_float, c_float, c_void_p]),
 }
 

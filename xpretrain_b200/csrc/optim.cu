@@ -143,9 +143,49 @@ opt_adamw_kernel(const XpOptTensor* __restrict__ table, const int2* __restrict__
   }
 }
 
+// Multi-tensor fp32 -> bf16 cast / fp32 copy over the same table: row.g = fp32 source, row.p_bf16 = bf16 destination
+// (or, when it is null, row.p = fp32 destination).  The models refresh ALL bf16 compute copies of a tower with one launch
+// per forward, so weights written behind autograd's back (`p.data.addcdiv_` of the reference AdamW, adamw.py:89,101;
+// EMA / checkpoint swaps) can never be stale.  HBM-bound: 6 B per parameter.
+__global__ void __launch_bounds__(OPT_THREADS)
+opt_cast_kernel(const XpOptTensor* __restrict__ table, const int2* __restrict__ blocks) {
+  const int2 e = blocks[blockIdx.x];
+  const XpOptTensor t = table[e.x];
+  const long long lo = static_cast<long long>(e.y) * OPT_CHUNK;
+  const long long hi = lo + OPT_CHUNK < t.n ? lo + OPT_CHUNK : t.n;
+  const float* src = static_cast<const float*>(t.g);
+  __nv_bfloat16* pb = static_cast<__nv_bfloat16*>(t.p_bf16);
+  float* pf = static_cast<float*>(t.p);
+  if (pb != nullptr) {
+    if (aligned16(src) && (reinterpret_cast<uintptr_t>(pb) & 7) == 0) {
+      for (long long i = lo + threadIdx.x * 4; i < hi; i += OPT_THREADS * 4) {
+        if (i + 4 <= hi) {
+          const float4 v = *reinterpret_cast<const float4*>(src + i);
+          *reinterpret_cast<uint2*>(pb + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        } else {
+          for (long long j = i; j < hi; ++j) pb[j] = __float2bfloat16(src[j]);
+        }
+      }
+    } else {
+      for (long long j = lo + threadIdx.x; j < hi; j += OPT_THREADS) pb[j] = __float2bfloat16(src[j]);
+    }
+  } else if (pf != nullptr) {
+    for (long long j = lo + threadIdx.x; j < hi; j += OPT_THREADS) pf[j] = src[j];
+  }
+}
+
 }  // namespace xp
 
 using namespace xp;
+
+extern "C" int xp_cast_table(const XpOptTensor* table_dev, const int32_t* block_map_dev, int32_t n_blocks, void* stream) {
+  XP_ENTER(table_dev);
+  if (n_blocks <= 0) return fail("xp_cast_table: empty block map");
+  opt_cast_kernel<<<n_blocks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      table_dev, reinterpret_cast<const int2*>(block_map_dev));
+  XP_CHECK_LAUNCH("opt_cast_kernel");
+  return 0;
+}
 
 extern "C" int32_t xp_opt_chunk_elems(void) { return OPT_CHUNK; }
 

@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib, ops
+from ._weights import WeightMirror
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -202,59 +203,58 @@ class CLIPModel(nn.Module):
 
 # -------------------------------------------------------------------- bf16 compute copies
 class _WeightPack:
-    """bf16 compute copies of one tower's GEMM weights with q/k/v fused to [3C, C]; refreshed from the fp32
-    master parameters whenever their version counters move (i.e. after an optimizer step)."""
+    """bf16 compute copies of one tower's GEMM weights with q/k/v fused to [3C, C] (+ the fused fp32 qkv bias)."""
 
-    def __init__(self, layers, device):
+    def __init__(self, layers, device, heads):
         L = len(layers)
         C_ = layers[0].self_attn.q_proj.weight.shape[0]
         I = layers[0].mlp.fc1.weight.shape[0]
         self.C, self.I, self.L = C_, I, L
+        self.q_scale = float(C_ // heads) ** -0.5          # CLIPAttention.scale = head_dim ** -0.5 (CLIP_ViP.py:245)
         self.wqkv = torch.empty(L, 3 * C_, C_, dtype=bf16, device=device)
         self.wo = torch.empty(L, C_, C_, dtype=bf16, device=device)
         self.w1 = torch.empty(L, I, C_, dtype=bf16, device=device)
         self.w2 = torch.empty(L, C_, I, dtype=bf16, device=device)
         self.bqkv = torch.empty(L, 3 * C_, dtype=f32, device=device)
-        self.version = None
 
-    def refresh(self, layers):
-        ver = tuple(p._version for layer in layers for p in layer.parameters())
-        if ver == self.version:
-            return
+    def items(self, layers):
         C_ = self.C
+        out = []
         for i, layer in enumerate(layers):
             a = layer.self_attn
             for j, lin in enumerate((a.q_proj, a.k_proj, a.v_proj)):
-                ops.cast_bf16(lin.weight.detach(), self.wqkv[i], dst_offset=j * C_ * C_)
-                self.bqkv[i, j * C_:(j + 1) * C_].copy_(lin.bias.detach())
-            ops.cast_bf16(a.out_proj.weight.detach(), self.wo[i])
-            ops.cast_bf16(layer.mlp.fc1.weight.detach(), self.w1[i])
-            ops.cast_bf16(layer.mlp.fc2.weight.detach(), self.w2[i])
-        self.version = ver
+                out.append((lin.weight, self.wqkv[i, j * C_:(j + 1) * C_]))
+                out.append((lin.bias, self.bqkv[i, j * C_:(j + 1) * C_]))
+            out += [(a.out_proj.weight, self.wo[i]), (layer.mlp.fc1.weight, self.w1[i]), (layer.mlp.fc2.weight, self.w2[i])]
+        return out
+
+
+def _refresh_weights(model: CLIPModel) -> None:
+    """Re-cast EVERY bf16 compute copy from the fp32 masters with one launch (modeling/_weights.py explains why this is
+    unconditional: in-place `p.data` writes of the reference's own optimizer must reach the next forward)."""
+    dev = model.logit_scale.device
+    pk = model._packs
+    if pk.get("device") != dev:
+        pk.clear()
+        pk["device"] = dev
+        pk["vision"] = _WeightPack(model.vision_model.encoder.layers, dev, model.config.vision.num_attention_heads)
+        pk["text"] = _WeightPack(model.text_model.encoder.layers, dev, model.config.text.num_attention_heads)
+        for key, p in (("small:patch", model.vision_model.embeddings.patch_embedding.weight),
+                       ("small:vproj", model.visual_projection.weight), ("small:tproj", model.text_projection.weight)):
+            pk[key] = torch.empty(p.shape, dtype=bf16, device=dev)
+        pk["mirror"] = WeightMirror()
+    items = pk["vision"].items(model.vision_model.encoder.layers) + pk["text"].items(model.text_model.encoder.layers)
+    items += [(model.vision_model.embeddings.patch_embedding.weight, pk["small:patch"]),
+              (model.visual_projection.weight, pk["small:vproj"]), (model.text_projection.weight, pk["small:tproj"])]
+    pk["mirror"].refresh(items)
 
 
 def _pack(model: CLIPModel, which: str) -> _WeightPack:
-    tower = model.vision_model if which == "vision" else model.text_model
-    layers = tower.encoder.layers
-    dev = layers[0].mlp.fc1.weight.device
-    pk = model._packs.get(which)
-    if pk is None or pk.wqkv.device != dev:
-        pk = _WeightPack(layers, dev)
-        model._packs[which] = pk
-    pk.refresh(layers)
-    return pk
+    return model._packs[which]
 
 
 def _small_bf16(model: CLIPModel, name: str, p: torch.Tensor) -> torch.Tensor:
-    key = "small:" + name
-    ent = model._packs.get(key)
-    if ent is None or ent[0].device != p.device:
-        ent = [torch.empty(p.shape, dtype=bf16, device=p.device), None]
-        model._packs[key] = ent
-    if ent[1] != p._version:
-        ops.cast_bf16(p.detach().contiguous(), ent[0])
-        ent[1] = p._version
-    return ent[0]
+    return model._packs["small:" + name]
 
 
 # --------------------------------------------------------------------------- encoder layers
@@ -268,7 +268,7 @@ def _layer_fwd(x, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, rows: in
     ops.layernorm_fwd(x, plain, h, plain, layer.layer_norm1.weight, layer.layer_norm1.bias, mean1, rstd1, rows, C_, eps)
     qkv = torch.empty(rows, 3 * C_, dtype=bf16, device=dev)
     # q = (h Wq^T + bq) * head_dim**-0.5 : the scale multiplies the bias too (CLIP_ViP.py:341 / :269)
-    ops.linear_fwd(h, pk.wqkv[i], pk.bqkv[i], qkv, scale_cols=C_, col_scale=0.125)
+    ops.linear_fwd(h, pk.wqkv[i], pk.bqkv[i], qkv, scale_cols=C_, col_scale=pk.q_scale)
     a = torch.empty(rows, C_, dtype=bf16, device=dev)
     att_saved = attn_fwd(qkv, a)
     x1 = torch.empty(rows, C_, dtype=bf16, device=dev)
@@ -459,7 +459,7 @@ def _vision_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str,
                       cls_map, grads["vision_model.post_layernorm.weight"], grads["vision_model.post_layernorm.bias"], B, C_)
 
     def attn_bwd(qkv, a, da, lse, dqkv):
-        ops.vip_attention_bwd(qkv, a, da, lse, dqkv, sv.ws, B, H, T, L, M, C_, 0.125)
+        ops.vip_attention_bwd(qkv, a, da, lse, dqkv, sv.ws, B, H, T, L, M, C_, pk.q_scale)
 
     timer = getattr(model, "block_timer", None)
     for i in reversed(range(len(vm.encoder.layers))):
@@ -502,11 +502,15 @@ def _text_fwd(model: CLIPModel, input_ids: torch.Tensor, attention_mask: Optiona
     dev = input_ids.device
     pk = _pack(model, "text")
     eps = cfg.layer_norm_eps
+    if Lt > cfg.max_position_embeddings:      # the reference fails in position_ids[:, :seq_length] + embedding add (CLIP_ViP.py:217-225)
+        raise ValueError(f"text length {Lt} exceeds max_position_embeddings {cfg.max_position_embeddings}")
     ids = input_ids.contiguous().to(torch.int64)
     mask = attention_mask.contiguous().to(torch.int64) if attention_mask is not None else None
     x = torch.empty(rows, C_, dtype=bf16, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     ops.text_embed_fwd(ids, tm.embeddings.token_embedding.weight, tm.embeddings.position_embedding.weight, x, Lt, err)
+    if getattr(model, "validate_ids", False) and int(err.item()) != 0:   # opt-in: costs a device sync per forward
+        raise IndexError("text_input_ids contains a token id outside [0, vocab_size) (nn.Embedding would raise, CLIP_ViP.py:222)")
 
     def attn_fwd(qkv, out):
         probs = torch.empty(B, H, Lt, Lt, dtype=f32, device=dev)
@@ -553,7 +557,7 @@ def _text_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str, t
                       grads["text_model.final_layer_norm.weight"], grads["text_model.final_layer_norm.bias"], B, C_)
 
     def attn_bwd(qkv, a, da, probs, dqkv):
-        ops.text_attention_bwd(qkv, da, probs, dqkv, B, H, Lt, C_, 0.125)
+        ops.text_attention_bwd(qkv, da, probs, dqkv, B, H, Lt, C_, pk.q_scale)
 
     for i in reversed(range(len(tm.encoder.layers))):
         prefix = f"text_model.encoder.layers.{i}."
@@ -567,9 +571,14 @@ def _text_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str, t
 # ------------------------------------------------------------------- the autograd.Function
 class _ClipVipFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model: CLIPModel, video, input_ids, attention_mask, normalize, *params):
-        save = any(ctx.needs_input_grad[5:])
+    def forward(ctx, model: CLIPModel, video, input_ids, attention_mask, normalize, grad_mode, *params):
+        # grad_mode = torch.is_grad_enabled() of the caller (Function.forward itself always runs under no_grad, and
+        # needs_input_grad reflects requires_grad even then): evaluation must not keep the activations alive
+        names = model._pnames
+        need = {n: r for n, r in zip(names, ctx.needs_input_grad[6:])}
+        save = grad_mode and any(need.values())
         ctx.model = model
+        _refresh_weights(model)
         ctx.normalize = normalize
         outs = []
         ctx.vis = ctx.txt = None
@@ -578,18 +587,21 @@ class _ClipVipFunction(torch.autograd.Function):
             if which == "vis":
                 if video is None:
                     outs.append(torch.empty(0, device=dev)); continue
-                proj, sv = _vision_fwd(model, video, save)
+                tower_save = save and any(r for n, r in need.items() if n.startswith(("vision_model.", "visual_projection.")))
+                proj, sv = _vision_fwd(model, video, tower_save)
             else:
                 if input_ids is None:
                     outs.append(torch.empty(0, device=dev)); continue
-                proj, sv = _text_fwd(model, input_ids, attention_mask, save)
+                # a frozen text tower (VidCLIP.freeze_text_encoder) keeps nothing and runs no backward
+                tower_save = save and any(r for n, r in need.items() if n.startswith(("text_model.", "text_projection.")))
+                proj, sv = _text_fwd(model, input_ids, attention_mask, tower_save)
             if normalize:
                 feat = torch.empty_like(proj)
                 inv = torch.empty(proj.shape[0], dtype=f32, device=dev)
                 ops.l2norm_fwd(proj, feat, inv)
             else:
                 feat, inv = proj, None
-            if save:
+            if sv is not None:
                 sv.feat, sv.inv = feat, inv
                 setattr(ctx, which, sv)
             outs.append(feat)
@@ -629,12 +641,13 @@ class _ClipVipFunction(torch.autograd.Function):
         if hook is not None and hasattr(hook, "finish"):
             hook.finish()      # stream-ordered wait: autograd's accumulation below sees the averaged values
         ctx.vis = ctx.txt = None
-        return (None, None, None, None, None) + tuple(grads.get(n) for n in names)
+        return (None, None, None, None, None, None) + tuple(grads.get(n) if r else None
+                                                             for n, r in zip(names, ctx.needs_input_grad[6:]))
 
 
 def _run(model: CLIPModel, video, input_ids, attention_mask, normalize: bool = True):
     if not model.logit_scale.is_cuda:
         raise _lib.XpError("xpretrain_b200.CLIPModel must live on a CUDA (B200) device: there is no CPU path")
     params = [p for n, p in model.named_parameters() if n != "logit_scale"]
-    vis, txt = _ClipVipFunction.apply(model, video, input_ids, attention_mask, normalize, *params)
+    vis, txt = _ClipVipFunction.apply(model, video, input_ids, attention_mask, normalize, torch.is_grad_enabled(), *params)
     return (vis if video is not None else None), (txt if input_ids is not None else None)

@@ -34,7 +34,7 @@ import torch.nn.functional as F
 
 from .. import _lib, ops
 from .clip_vip import _alloc_flat
-from .timesformer import _linear_bwd, _w
+from .timesformer import _linear_bwd, _w, refresh_weights
 
 bf16, f32 = torch.bfloat16, torch.float32
 HEAD_DIM = 32
@@ -373,6 +373,7 @@ class _Swin3DFunction(torch.autograd.Function):
         if Cin != 3 or Hin % ph or Win % pw:
             raise ValueError("video must be [B, 3, D, H, W] with H, W divisible by the patch size")
         save = any(ctx.needs_input_grad[4:])
+        refresh_weights(model)
         dev = video.device
         C0 = model.embed_dim
         # ---- PatchEmbed3D (:431-448): frames x (h, w) patches, rows already in (b, d, h, w) order

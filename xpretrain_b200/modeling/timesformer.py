@@ -133,16 +133,25 @@ class TimeSformer(nn.Module):
 
 
 # ----------------------------------------------------------------------------------- helpers
-def _w(model: TimeSformer, name: str, p: torch.Tensor) -> torch.Tensor:
-    """bf16 compute copy of a GEMM weight, refreshed when the fp32 master's version counter moves."""
-    ent = model._cache.get(name)
-    if ent is None or ent[0].device != p.device:
-        ent = [torch.empty(p.shape, dtype=bf16, device=p.device), None]
-        model._cache[name] = ent
-    if ent[1] != p._version:
-        ops.cast_bf16(p.detach().contiguous(), ent[0])
-        ent[1] = p._version
-    return ent[0]
+def _w(model, name: str, p: torch.Tensor) -> torch.Tensor:
+    """bf16 compute copy of a GEMM weight (refreshed for the whole model at the start of every forward)."""
+    return model._cache[name]
+
+
+def refresh_weights(model) -> None:
+    """Re-cast every GEMM weight (parameters with >= 2 dims that `_w` serves) with ONE launch on every forward: in-place
+    `p.data` updates of the reference optimizers do not move `_version`, so no validity test is used (modeling/_weights.py)."""
+    from ._weights import WeightMirror
+    cache = model._cache
+    named = [(n, p) for n, p in model.named_parameters() if p.dim() >= 2 and n.endswith("weight")]
+    dev = named[0][1].device
+    if cache.get("__device__") != dev:
+        cache.clear()
+        cache["__device__"] = dev
+        cache["__mirror__"] = WeightMirror()
+        for n, p in named:
+            cache[n] = torch.empty(p.shape, dtype=bf16, device=dev)
+    cache["__mirror__"].refresh([(p, cache[n]) for n, p in named])
 
 
 def _tables(model: TimeSformer, T: int, H: int, W: int, pos_param=None, time_param=None):
@@ -305,6 +314,7 @@ class _TimeSformerFunction(torch.autograd.Function):
             raise ValueError(f"expected {model.embed_dim} channels, got {C_}")
         HW, rows = H * W, B * H * W * T
         save = any(ctx.needs_input_grad[3:])
+        refresh_weights(model)
         x = x.contiguous()
         pos_tab, time_tab = _tables(model, T, H, W)
         tok = torch.empty(rows, C_, dtype=bf16, device=x.device)

@@ -50,14 +50,18 @@ def _nce_backward(g, vh, th, row0: int, nrows: int, scale: float):
     Np = g.shape[1]
     dev = g.device
     d_vis = torch.empty(nrows, d, dtype=f32, device=dev)
-    d_txt = torch.empty(nrows, d, dtype=f32, device=dev)
     # A = G rows (K-major), B = T stored [K=N, d] (MN-major)
     ops.gemm(g, th, d_vis, M=nrows, N=d, K=N, lda=Np, ldb=d, ldc=d, b_layout=1, out_mode=_lib.OUT_F32, alpha=scale,
              a_offset=row0 * Np)
-    # A = G^T: stored [K=N(i), M=N(j)] -> MN-major A, columns row0.. ; B = V stored [K=N, d]
-    ops.gemm(g, vh, d_txt, M=nrows, N=d, K=N, lda=Np, ldb=d, ldc=d, a_layout=1, b_layout=1, out_mode=_lib.OUT_F32,
-             alpha=scale, a_offset=row0)
-    return d_vis, d_txt
+    # A = G^T: stored [K=N(i), M=N(j)] -> MN-major A, columns row0.. ; B = V stored [K=N, d].  The TMA base must be
+    # 16-byte aligned, so the column window starts at row0 rounded down to 8 and the slack rows are sliced off
+    # (a per-rank batch that is not a multiple of 8 used to fail on ranks >= 1).
+    r0 = row0 // 8 * 8
+    ext = row0 - r0 + nrows
+    d_txt = torch.empty(ext, d, dtype=f32, device=dev)
+    ops.gemm(g, vh, d_txt, M=ext, N=d, K=N, lda=Np, ldb=d, ldc=d, a_layout=1, b_layout=1, out_mode=_lib.OUT_F32,
+             alpha=scale, a_offset=r0)
+    return d_vis, d_txt[row0 - r0:]
 
 
 class _NceFunction(torch.autograd.Function):
