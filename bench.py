@@ -267,9 +267,22 @@ def run_ours(args):
         n_par = sum(p.numel() for p in params)
         o_ms = o0.elapsed_time(o1) / 5
         hbm = measured_peaks().get("hbm_gbs", 6576.4)
+        # a complete training step: fwd (incl. the per-forward fp32 -> bf16 weight re-cast) + gather + loss + bwd + clip + AdamW
+        for _ in range(2):
+            step(*resident[0]); opt.step(max_grad_norm=5.0)
+        torch.cuda.synchronize()
+        o2, o3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o2.record()
+        for i in range(4):
+            step(*resident[i % n_host]); opt.step(max_grad_norm=5.0)
+        o3.record()
+        torch.cuda.synchronize()
+        t_ms = o2.elapsed_time(o3) / 4
         opt_info = {"what": "global-norm clip + AdamW over all parameters, 3 kernel launches", "ms": round(o_ms, 3),
                     "params": n_par, "gbs": round(32.0 * n_par / o_ms / 1e6, 1), "hbm_peak_gbs": hbm,
-                    "frac_of_hbm_peak": round(32.0 * n_par / o_ms / 1e6 / hbm, 3)}
+                    "frac_of_hbm_peak": round(32.0 * n_par / o_ms / 1e6 / hbm, 3),
+                    "train_step": {"what": "fwd + gather + InfoNCE + bwd + clip + AdamW (lr 0), inputs resident",
+                                   "ms": round(t_ms, 3), "pairs_per_s": round(B / t_ms * 1e3, 2)}}
         del opt
 
     if rank != 0:
@@ -303,7 +316,13 @@ def run_ours(args):
                        "frac_of_peak": round(value / world * fm["train"] / 1e12 / peaks["tflops"], 4)},
     }
     if world == 1:
-        line["cpu_baseline"] = cpu_baseline(steps=1, warmup=1, batch=args.cpu_batch)
+        line["cpu_baseline"] = cpu_baseline(steps=CPU_MIN_STEPS, warmup=1, batch=CPU_BATCH)
+        if not args.no_eager:
+            del model, resident, slots
+            torch.cuda.empty_cache()
+            line["gpu_eager_baseline"] = gpu_eager_baseline(dev, B)
+            if "value" in line["gpu_eager_baseline"]:
+                line["gpu_eager_baseline"]["ours_over_eager_e2e"] = round(e2e_value / line["gpu_eager_baseline"]["value"], 2)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -344,49 +363,303 @@ def cpu_step_fn(batch):
     return fn
 
 
-def cpu_baseline(steps, warmup, batch):
+CPU_BATCH, CPU_THREADS_MAX, CPU_MIN_STEPS = 2, 32, 3
+
+
+def cpu_threads():
+    return min(os.cpu_count() or 1, CPU_THREADS_MAX)
+
+
+def cpu_baseline(steps, warmup, batch=CPU_BATCH):
+    """The reference algorithm on the host: FIXED batch and thread count, median of >= 3 timed steps, identical in the
+    in-line `cpu_baseline` object and in `--impl reference` (the one-step probe made the denominator swing 5x)."""
     import torch
     cores = os.cpu_count() or 1
-    threads = min(cores, 64)
+    threads = cpu_threads()
     torch.set_num_threads(threads)
     fn = cpu_step_fn(batch)
-    for _ in range(warmup):
+    for _ in range(max(1, warmup)):
         fn()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    times = []
+    for _ in range(max(CPU_MIN_STEPS, steps)):
+        t0 = time.perf_counter()
         fn()
-    dt = (time.perf_counter() - t0) / steps
+        times.append(time.perf_counter() - t0)
+    dt = statistics.median(times)
     return {"value": round(batch / dt, 3), "unit": UNIT, "cores": threads, "host_cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of batch {batch} x {T_FRAMES} frames x 224^2 + {L_TOK} tok, 12+12 layers, fp32 eager "
-                      f"fwd+loss+bwd (oracle/clipvip_oracle.py, pinned to the reference by tests/golden/make_golden.py)",
-            "seconds_per_step": round(dt, 3)}
+            "sample": f"median of {len(times)} steps of batch {batch} x {T_FRAMES} frames x 224^2 + {L_TOK} tok, 12+12 layers, fp32 "
+                      f"eager fwd+loss+bwd on {threads} threads (oracle/clipvip_oracle.py, pinned to the reference by "
+                      f"tests/golden/make_golden.py)",
+            "seconds_per_step": round(dt, 3), "seconds_min_max": [round(min(times), 3), round(max(times), 3)]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: pick the pairs per step so that W + K steps end within ~4 minutes on this host (probe: one pair)
-    import torch
-    torch.set_num_threads(min(os.cpu_count() or 1, 64))
-    probe = cpu_step_fn(1)
-    t0 = time.perf_counter()
-    probe()
-    per_pair = time.perf_counter() - t0
-    del probe
-    budget = 240.0 / max(1, args.steps + args.warmup)
-    args.cpu_batch = next((b for b in (args.cpu_batch, 2, 1) if b <= args.cpu_batch and b * per_pair <= budget), 1)
-    base = cpu_baseline(steps=args.steps, warmup=args.warmup, batch=args.cpu_batch)
+    if args.workload != "clipvip":
+        return run_reference_encoder(args)
+    steps = min(max(args.steps, CPU_MIN_STEPS), 12)     # bounded: ~5 s per step of batch 2
+    base = cpu_baseline(steps=steps, warmup=min(args.warmup, 2), batch=CPU_BATCH)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(base["seconds_per_step"] * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"CLIP-ViP ViT-B/16, {T_FRAMES} frames x 224^2, {L_TOK} tok; each step a bounded sample "
-                                   f"of batch {args.cpu_batch} on the host CPU (the reference is pure PyTorch; its own "
-                                   f"CPU path = fp32 eager)", "global_batch": args.cpu_batch, "parallelism": "cpu"},
+                                   f"of batch {CPU_BATCH} on the host CPU (the reference is pure PyTorch; its own "
+                                   f"CPU path = fp32 eager); value = median step", "global_batch": CPU_BATCH,
+                       "parallelism": "cpu", "timed_steps": steps},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(dev, batch):
+    """north_star's 1-GPU bar, measured by the same run: the reference algorithm (oracle port: the same torch ops in the same
+    order as CLIP_ViP.py / loss.py) in PyTorch eager on THIS B200 under bf16 autocast (`.to(bf16)` crashes in the reference,
+    SURVEY.md §8c), fwd + InfoNCE + bwd, 2 warm-up + 3 timed steps; falls back to a smaller batch when eager runs out of memory."""
+    import torch
+    from oracle import clipvip_oracle as O
+    cfg = O.ClipVipCfg()
+    for B in (batch, batch // 2, batch // 4):
+        if B < 1:
+            break
+        try:
+            sd = {k: (v.to(dev).requires_grad_(True) if v.is_floating_point() else v.to(dev))
+                  for k, v in O.init_state_dict(cfg, seed=0).items()}
+            video, ids, mask = (t.to(dev) for t in O.synthetic_batch(B, T_FRAMES, L_TOK, cfg, seed=1234))
+
+            def step():
+                for v in sd.values():
+                    if v.is_floating_point():
+                        v.grad = None
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    out = O.clip_vip_forward(sd, video, ids, mask, cfg)
+                    loss = O.nce_learnable_temp_loss(out["vis_features"].float(), out["text_features"].float(), sd["logit_scale"])
+                loss.backward()
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            return {"what": "reference algorithm (oracle port), PyTorch eager, bf16 autocast, same GPU, same workload",
+                    "batch": B, "ms_per_step": round(ms, 2), "value": round(B / ms * 1e3, 2), "unit": UNIT,
+                    "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1)}
+        except torch.OutOfMemoryError:
+            sd = video = None
+            torch.cuda.empty_cache()
+    return {"what": "reference algorithm in PyTorch eager", "error": "out of memory at every batch tried"}
+
+
+# ------------------------------------------------------- configs[3] / configs[4]: the video encoders of HD-VILA / LF-VILA
+ENCODERS = {
+    "timesformer": dict(
+        metric="video clips/sec, HD-VILA TimeSformer (depth 4, dim 1024, 16 heads) fwd+bwd", unit="clips/s", batch=16,
+        shape="[16, 8, 1024, 7, 7] = BASELINE.json configs[3]: 8 frames x 448^2 -> 7x7 feature grid (both table interpolations), "
+              "batch 16/GPU"),
+    "swin3d": dict(
+        metric="videos/sec, LF-VILA Swin-3D video encoder (released VideoEncoder config) fwd+bwd", unit="videos/s", batch=8,
+        shape="[8, 3, 32, 224, 224] = BASELINE.json configs[4]: 32 frames x 224^2, batch 8/GPU"),
+}
+
+
+def _encoder_flops(kind):
+    """FLOP accounting only, read after the timed region."""
+    if kind == "timesformer":
+        from oracle import timesformer_oracle as TO
+        return TO.flops_per_sample(TO.TimeSformerCfg(), 8, 7, 7)
+    from oracle import swin3d_oracle as SO
+    return SO.flops_per_sample(SO.Swin3DCfg(), 32, 224, 224)
+
+
+def _encoder_ours(kind, dev, batch, seed):
+    """(module with its own random init, pinned host input, weighted-sum target, forward) — nothing from oracle/ here."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(0)
+    if kind == "timesformer":
+        from xpretrain_b200.modeling.timesformer import TimeSformer
+        model = TimeSformer(depth=4, num_frames=7, H=10, W=16, embed_dim=1024, num_heads=16, drop_path_rate=0.0).to(dev).train()
+        x = torch.randn(batch, 8, 1024, 7, 7, generator=g)
+        fwd = lambda m, xin: m(xin)                                              # noqa: E731
+    else:
+        from xpretrain_b200.modeling.swin3d import SwinTransformer3D
+        model = SwinTransformer3D(patch_norm=True, local_window=8, drop_path_rate=0.0).to(dev).train()
+        x = torch.randn(batch, 3, 32, 224, 224, generator=g)
+        fwd = lambda m, xin: m(xin)[0]                                           # noqa: E731
+    with torch.no_grad():
+        oshape = fwd(model, x[:1].to(dev)).shape
+    n_out = 1
+    for v in oshape[1:]:
+        n_out *= v
+    w_out = torch.randn((batch,) + tuple(oshape[1:]), generator=g) / float(n_out) ** 0.5
+    return model, x, w_out, fwd
+
+
+def _encoder_oracle(kind, batch, seed):
+    import torch
+    g = torch.Generator().manual_seed(7)
+    if kind == "timesformer":
+        from oracle import timesformer_oracle as TO
+        cfg = TO.TimeSformerCfg()
+        sd = TO.init_state_dict(cfg, seed=0)
+        x = TO.synthetic_input(batch, 8, 7, 7, cfg, seed=seed)
+        w_out = torch.randn(batch, 8, cfg.embed_dim, 7, 7, generator=g) / (batch * 8 * 49) ** 0.5
+        return sd, x, w_out, (lambda sdo, xin: TO.timesformer_forward(sdo, xin, cfg))
+    from oracle import swin3d_oracle as SO
+    cfg = SO.Swin3DCfg()
+    sd = SO.init_state_dict(cfg, seed=0)
+    x = SO.synthetic_video(batch, 32, 224, 224, cfg, seed=seed)
+    oshape = (batch, 32, 224 // 64, 224 // 64, 1024)
+    w_out = torch.randn(oshape, generator=g) / (32 * 3 * 3 * 1024) ** 0.5
+    return sd, x, w_out, (lambda sdo, xin: SO.swin3d_forward(sdo, xin, cfg))
+
+
+def encoder_cpu_baseline(kind, steps, warmup):
+    """The reference encoder algorithm (oracle port, pinned bit-exact to the reference class by tests/golden/make_golden_*.py)
+    on the host cores: fwd + bwd of a bounded sample (timesformer: 2 clips; swin3d: 1 video), median of >= 3 steps."""
+    import torch
+    batch = 2 if kind == "timesformer" else 1
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
+    sd, x, w_out, oracle_fwd = _encoder_oracle(kind, batch, seed=1)
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+
+    def fn():
+        for v in sdo.values():
+            if v.is_floating_point():
+                v.grad = None
+        (oracle_fwd(sdo, x) * w_out).sum().backward()
+
+    for _ in range(max(1, warmup)):
+        fn()
+    times = []
+    for _ in range(max(CPU_MIN_STEPS, steps)):
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    dt = statistics.median(times)
+    return {"value": round(batch / dt, 3), "unit": ENCODERS[kind]["unit"], "cores": threads, "host_cores": os.cpu_count() or 1,
+            "kind": "port", "seconds_per_step": round(dt, 3),
+            "sample": f"median of {len(times)} steps of batch {batch}, fp32 eager fwd+bwd of the oracle port on {threads} threads"}
+
+
+def run_reference_encoder(args):
+    kind = args.workload
+    base = encoder_cpu_baseline(kind, steps=min(max(args.steps, CPU_MIN_STEPS), 8), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": ENCODERS[kind]["metric"], "value": base["value"], "unit": base["unit"],
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(base["seconds_per_step"] * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": ENCODERS[kind]["shape"] + "; each step a bounded CPU sample", "parallelism": "cpu"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": base["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_encoder(args):
+    """`--workload timesformer|swin3d`: the same JSON contract for BASELINE.json configs[3] / configs[4]."""
+    import torch
+    import torch.distributed as dist
+    from xpretrain_b200 import ops
+    from xpretrain_b200.utils import distributed as xdist
+
+    kind = args.workload
+    rank, local, world = xdist.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = ENCODERS[kind]["batch"] if args.batch == PER_GPU_BATCH else args.batch
+    model, x_host, w_out, fwd = _encoder_ours(kind, dev, B, seed=1 + rank)
+    params = list(model.parameters())
+    x_host = x_host.pin_memory()
+    x_dev, w_out = x_host.to(dev), w_out.to(dev)
+
+    def step(xin):
+        for p in params:
+            p.grad = None
+        loss = (fwd(model, xin) * w_out).sum()
+        loss.backward()
+        if world > 1:       # independent samples: data-parallel replicas, gradients averaged (hvd.DistributedOptimizer semantics)
+            xdist.average_gradients(params)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms_res = timed(lambda i: step(x_dev), args.steps)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    last = {}
+
+    def e2e_step(i):
+        xin = x_host.to(dev, non_blocking=True)
+        last["loss"] = step(xin).detach().item()
+
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    rec = []
+    ops.set_gemm_timer(rec)
+    step(x_dev)
+    torch.cuda.synchronize()
+    ops.set_gemm_timer(None)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    g_ms = sum(a.elapsed_time(b) for (_, a, b) in rec)
+    g_fl = sum(f for (f, _, _) in rec)
+    peaks = measured_peaks()
+    flops = _encoder_flops(kind)
+    ach = g_fl / (g_ms * 1e-3) / 1e12
+    value, e2e_value = B * world / (ms_res * 1e-3), B * world / (ms_e2e * 1e-3)
+    line = {"metric": ENCODERS[kind]["metric"], "value": round(value, 2), "unit": ENCODERS[kind]["unit"], "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": ENCODERS[kind]["shape"] + "; step = fwd + weighted-sum loss + bwd"
+                                   + (" + DP gradient all-reduce" if world > 1 else ""),
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "activations per step far exceed the 126 MB L2", "weights": "random init (reference statistics)"},
+            "e2e": {"value": round(e2e_value, 2), "unit": ENCODERS[kind]["unit"], "ms_per_step": round(ms_e2e, 3),
+                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": 4,
+                    "last_loss": last.get("loss")},
+            "gpu_launches": int(launches * world), "clocks": clocks,
+            "roofline": {"kernel": "xp::gemm_kernel (tcgen05 bf16, all launches of one step)", "bound": "tensor",
+                         "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": round(ach / peaks["tflops"], 4),
+                         "traffic": None, "peak_source": peaks["source"], "launches_per_step": len(rec),
+                         "gemm_ms_per_step": round(g_ms, 3), "gemm_share_of_step": round(g_ms / ms_res, 4)},
+            "whole_step": {"flops_per_sample": 3.0 * flops, "tflops_per_gpu": round(value / world * 3.0 * flops / 1e12, 1),
+                           "frac_of_peak": round(value / world * 3.0 * flops / 1e12 / peaks["tflops"], 4)}}
+    if world == 1:
+        line["cpu_baseline"] = encoder_cpu_baseline(kind, steps=CPU_MIN_STEPS, warmup=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -396,12 +669,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE.json configs[1]: 64)")
-    ap.add_argument("--cpu-batch", type=int, default=4, help="pairs per CPU-baseline step (bounded sample)")
+    ap.add_argument("--workload", default="clipvip", choices=["clipvip", "timesformer", "swin3d"],
+                    help="clipvip = BASELINE.json configs[1]/[2] (default, the headline); timesformer = configs[3] (HD-VILA "
+                         "spatio-temporal encoder); swin3d = configs[4] (LF-VILA Swin-3D video encoder)")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.workload == "clipvip":
         run_ours(args)
+    else:
+        run_encoder(args)
 
 
 if __name__ == "__main__":

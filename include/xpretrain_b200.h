@@ -180,6 +180,37 @@ int xp_text_attention_bwd(const void* qkv, const void* dout, const float* probs,
 int xp_nce_split(const float* x, void* x3_bf16, void* hi_bf16, int32_t rows, int32_t d, int32_t pattern, void* stream);
 int xp_nce_softmax_grad(const float* z, const float* logit_scale, float* lse_rows, float* lse_cols, void* g_scaled_bf16,
                         float* loss, float* d_logit_scale, int32_t N, int64_t ld, void* stream);
+/* Fused exchange + loss: replaces `hvd.allgather(vis)`, `hvd.allgather(txt)` (CLIP-ViP/src/pretrain/run_pretrain.py:344-345;
+ * rank-major concat, semantics pinned by LF-VILA/src/utils/dist.py:21-41) AND NCELearnableTempLoss.forward (loss.py:134-141)
+ * with ONE cooperative kernel (csrc/nce_fused.cu): device-side flag barrier over peer-mapped exchange buffers, logits tiles
+ * on tcgen05 whose operand rows are loaded straight from the owning peer's memory over NVLink (hi/lo split in the producer),
+ * row/column log-sum-exps, loss (overwritten), d logit_scale (overwritten), g_scaled bf16 [N, ld_g] = exp(logit_scale)*dL/dZ,
+ * and the bf16 copies vis_hi / txt_hi [N, d] that the local gradient GEMMs use.  N = world * b <= 1536.
+ *   mode 0: peer_bufs = device array of `world` exchange-buffer base pointers (own buffer at [rank]); every buffer is
+ *           xp_nce_gather_exchange_bytes() large, zero-initialised once, and mapped by all ranks (symmetric memory);
+ *           vis_local / txt_local fp32 [b, d] are published by the kernel; `epoch` must increase by 1 per call (from 1).
+ *   mode 1: no exchange: peer_bufs = device array of 2*world pointers, [r] = rank r's vis rows, [world + r] = its txt rows
+ *           (fp32 [b, d]) in local memory (single process, or rows pre-gathered by another transport).
+ * workspace: xp_nce_gather_workspace_bytes(N) bytes, zero-initialised once (it holds the kernel's barrier counters). */
+typedef struct XpNceGather {
+  const float* vis_local;
+  const float* txt_local;
+  void* const* peer_bufs;
+  const float* logit_scale;
+  void* g_scaled;
+  void* vis_hi;
+  void* txt_hi;
+  float* loss;
+  float* d_logit_scale;
+  float* workspace;
+  int32_t rank, world, b, d;
+  uint32_t epoch;
+  int32_t mode;
+  int64_t ld_g;
+} XpNceGather;
+int64_t xp_nce_gather_exchange_bytes(int32_t b, int32_t d, int32_t world);
+int64_t xp_nce_gather_workspace_bytes(int32_t N);
+int xp_nce_gather_fused(const XpNceGather* args, void* stream);
 /* NCELearnableTempLoss_vsc_fc.forward, CLIP-ViP/src/optimization/loss.py:288-324 (the released pre-training default:
  * video x subtitle, video x caption, frame x caption): za = V T^T, zb = V C^T, zd = I C^T, fp32 [N, N] with row pitch ld,
  * unscaled.  Writes the scalar loss (overwritten), ACCUMULATES d_logit_scale, and the three gradient matrices

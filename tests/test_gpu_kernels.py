@@ -240,7 +240,9 @@ def _vip_ref(qkv, B, H, T, L, M, C):
     return o.transpose(1, 2).reshape(B * S, C), torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("B,H,T,L,M", [(2, 2, 3, 196, 4), (1, 12, 2, 196, 4), (2, 1, 4, 20, 2), (1, 2, 1, 196, 4)])
+@pytest.mark.parametrize("B,H,T,L,M", [(2, 2, 3, 196, 4), (1, 12, 2, 196, 4), (2, 1, 4, 20, 2), (1, 2, 1, 196, 4),
+                                       (3, 12, 12, 196, 4),      # 432 items: every persistent CTA pipelines across several items
+                                       (2, 3, 5, 130, 1), (2, 2, 3, 128, 8), (2, 2, 2, 100, 3)])
 def test_vip_attention_fwd_bwd(dev, B, H, T, L, M):
     from xpretrain_b200 import ops
     C, S = 64 * H, M + T * L
@@ -305,6 +307,58 @@ def test_text_attention_fwd_bwd(dev, Lt):
 
 
 # ------------------------------------------------------------------------------------------------ NCE
+@pytest.mark.parametrize("world,b", [(4, 8), (8, 64), (3, 50), (8, 192), (2, 3)])
+def test_fused_gather_nce_kernel_rank_major_rows_and_unfused_path(dev, world, b, golden_dir):
+    """csrc/nce_fused.cu in pre-gathered mode on one GPU: `world` per-rank [b, d] blocks living in separate allocations are
+    read through the pointer table in rank-major order (hvd.allgather's concat order, run_pretrain.py:344-345).  Checked
+    against the reference-class golden (world 4 x 8), the oracle, and the unfused multi-launch path on the same rows."""
+    from oracle import clipvip_oracle as O
+    from xpretrain_b200 import _lib
+    from xpretrain_b200.optimization import loss as XL
+    d, N = 512, world * b
+    if (world, b) == (4, 8):
+        gold = torch.load(os.path.join(golden_dir, "nce_loss_w4.pt"), weights_only=False)
+        vis, txt, temp = gold["vis_per_rank"], gold["txt_per_rank"], gold["logit_scale"]
+    else:
+        g = torch.Generator(device="cpu").manual_seed(N)
+        vis = [F.normalize(torch.randn(b, d, generator=g), dim=-1) for _ in range(world)]
+        txt = [F.normalize(torch.randn(b, d, generator=g) + 0.5 * v, dim=-1) for v in vis]
+        temp = torch.tensor(4.6)
+    V, T = O.gather_rank_major(vis), O.gather_rank_major(txt)
+    dv, dt, dl = O.nce_closed_form_grads(V, T, temp)
+    want = float(O.nce_learnable_temp_loss(V, T, temp))
+    if (world, b) == (4, 8):
+        assert abs(want - float(gold["loss"])) < 1e-6 and rel(dv, gold["d_vis"]) < 1e-5
+    dvis = [x.to(dev) for x in vis]
+    dtxt = [x.to(dev) for x in txt]
+    ptrs = torch.tensor([x.data_ptr() for x in dvis] + [x.data_ptr() for x in dtxt], dtype=torch.int64, device=dev)
+    Np = (N + 7) // 8 * 8
+    gmat = torch.zeros(N, Np, dtype=bf16, device=dev)
+    vh, th = torch.empty(N, d, dtype=bf16, device=dev), torch.empty(N, d, dtype=bf16, device=dev)
+    loss, dscale = torch.empty(1, device=dev), torch.empty(1, device=dev)
+    ws = torch.zeros(int(_lib.lib().xp_nce_gather_workspace_bytes(N)) // 4, device=dev)
+    tdev = temp.reshape(1).to(dev)
+    a = _lib.XpNceGather()
+    a.logit_scale, a.g_scaled, a.vis_hi, a.txt_hi = tdev.data_ptr(), gmat.data_ptr(), vh.data_ptr(), th.data_ptr()
+    a.loss, a.d_logit_scale, a.workspace, a.peer_bufs = loss.data_ptr(), dscale.data_ptr(), ws.data_ptr(), ptrs.data_ptr()
+    a.rank, a.world, a.b, a.d, a.mode, a.epoch, a.ld_g = 0, world, b, d, 1, 0, Np
+    import ctypes
+    for _ in range(2):           # twice: the kernel must leave its barrier counters reset
+        _lib.check(_lib.lib().xp_nce_gather_fused(ctypes.byref(a), torch.cuda.current_stream().cuda_stream), "xp_nce_gather_fused")
+    torch.cuda.synchronize()
+    s = float(temp.exp())
+    P = torch.softmax(s * V @ T.t(), 1) + torch.softmax(s * V @ T.t(), 0) - 2 * torch.eye(N)
+    assert abs(float(loss) - want) < 2e-5 * max(1.0, abs(want))                     # fp32-grade logits (hi/lo split)
+    assert abs(float(dscale) - float(dl)) < 1e-3 * max(1.0, abs(float(dl)))
+    assert rel(gmat[:, :N].float().cpu(), s * P / N) < 5e-3                          # bf16 storage of G
+    assert torch.equal(vh.cpu(), V.to(bf16)) and torch.equal(th.cpu(), T.to(bf16))   # rank-major rows, bit-exact
+    # the unfused path on the same gathered rows
+    l2, g2, _, _, ds2 = XL._nce_forward_unfused(V.to(dev), T.to(dev), temp.to(dev))
+    assert abs(float(l2) - float(loss)) < 2e-5 * max(1.0, abs(want)) and rel(g2[:, :N].float(), gmat[:, :N].float()) < 5e-3
+    d_vis, d_txt = XL._nce_backward(gmat, vh, th, 0, N, 1.0)
+    assert rel(d_vis.cpu(), dv) < 6e-3 and rel(d_txt.cpu(), dt) < 6e-3
+
+
 @pytest.mark.parametrize("N", [8, 64, 512, 6])
 def test_nce_loss_and_grads(dev, N):
     from oracle import clipvip_oracle as O

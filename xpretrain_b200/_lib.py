@@ -38,6 +38,13 @@ class XpSegAttn(C.Structure):
                 ("bias_windows", c_int), ("head_dim", c_int)]
 
 
+class XpNceGather(C.Structure):
+    _fields_ = [("vis_local", c_void_p), ("txt_local", c_void_p), ("peer_bufs", c_void_p), ("logit_scale", c_void_p),
+                ("g_scaled", c_void_p), ("vis_hi", c_void_p), ("txt_hi", c_void_p), ("loss", c_void_p),
+                ("d_logit_scale", c_void_p), ("workspace", c_void_p), ("rank", c_int), ("world", c_int), ("b", c_int),
+                ("d", c_int), ("epoch", C.c_uint32), ("mode", c_int), ("ld_g", c_i64)]
+
+
 ACT_NONE, ACT_QUICK_GELU, ACT_DQUICK_GELU, ACT_GELU_ERF, ACT_DGELU_ERF = 0, 1, 2, 3, 4
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
@@ -86,6 +93,9 @@ SIGNATURES = {
     "xp_nce_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "xp_nce_softmax_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_i64, c_void_p]),
+    "xp_nce_gather_exchange_bytes": (c_i64, [c_int, c_int, c_int]),
+    "xp_nce_gather_workspace_bytes": (c_i64, [c_int]),
+    "xp_nce_gather_fused": (c_int, [P(XpNceGather), c_void_p]),
     "xp_nce_vsc_fc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_i64, c_void_p]),
     "xp_seg_attention_fwd":(c_int, [c_void_p, c_void_p, c_void_p, P(XpSegAttn), c_void_p]),

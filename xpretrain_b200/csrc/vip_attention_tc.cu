@@ -328,34 +328,49 @@ extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float
 }
 
 // =====================================================================================================
-// Backward.  Persistent, one CTA per SM, 14 warps:
-//   warps 0,2,3,12  producers (cp.async): Q' / dO' rows (same row layout as forward), K' (+global), V' (+global),
-//                   and lse / delta of the query rows
-//   warp 1          MMA issuer (one thread)
-//   warps 4-11      two math warpgroups: thread = query row of the current 128-row q tile; WG A owns key
-//                   columns [0,64) of the step, WG B columns [64,128); in the epilogues WG A drains dV and dQ_0,
-//                   WG B dK and dQ_1
-// A problem = 2 key tiles x 2 query tiles = 4 steps of [128 q x 128 keys]:
+// Backward (round 2: software-pipelined).  Persistent, one CTA per SM, 20 warps:
+//   warp 0        TMA producer (one thread): per item, five independently released operand groups —
+//                 K' (+global keys; DOUBLE-buffered across items), Q'/dO' rows [0,128) ("q0"), Q'/dO' rows [128,L) + the
+//                 M global rows ("q1"), V' keys [0,128) ("v0"), V' keys [128,L) + global ("v1") — so that the next item's
+//                 first step is already staged while the current item's last steps run
+//   warp 1        MMA issuer (one thread)
+//   warp 2        TMEM allocator
+//   warps 4-19    four math warpgroups; thread = query row (TMEM lane) of the current 128-row query tile, warpgroup g
+//                 owns key columns [32g, 32g+32) of the step
+// An item = (batch b, head h, frame t) = 2 key tiles x 2 query tiles = 4 steps of [128 q x 128 keys] (s = 2 i + j):
 //   S  = Q_j K_i^T, dP = dO_j V_i^T                (tcgen05.mma SS -> TMEM columns [0,128), [128,256))
-//   P  = exp(S - lse), dS = P * (dP - delta)       (threads; bf16 P and dS written to shared memory, SWIZZLE_128B)
-//   dV_i += P^T dO_j, dK_i += dS^T Q_j             (A = P / dS read MN-major from shared memory; TMEM [256,384))
-//   dQ_j += dS K_i                                 (A = dS read K-major; TMEM [384,512))
-// Key tile 0 = frame keys [0,128); key tile 1 = frame keys [128,208) in columns [0,80) + the M global keys in
-// columns [80,96).  Query tile 0 = frame rows [0,128); tile 1 = frame rows [128,196) + global rows at 200..
-// delta_i = sum_d dO_id O_id is precomputed (vip_attn_delta_kernel).  The gradients of the M global rows are
-// emitted as per-frame fp32 partials and reduced by vip_attn_bwd_combine (vip_attention.cu).
-constexpr int TB_THREADS = 448;
+//   phase 1: P = exp(S - lse) kept as packed bf16 in REGISTERS -> the S columns are released at once, so S of step
+//            n+1 is computed while phase 2 of step n runs
+//   phase 2: dS = P * (dP - delta); P and dS (bf16) written to shared memory, SWIZZLE_128B
+//   G:  dV_i += P^T dO_j, dK_i += dS^T Q_j (A MN-major from smem; TMEM [256,384)); dQ_j += dS K_i (TMEM [384,512))
+// Issue order per step n: S_n | dP_n | G_(n-1): the tensor pipe works on dP_n and the three gradient products of the
+// previous step while the math warps are in phase 1 of step n, and on S_(n+1) during their phase 2.  Accumulators are
+// drained (dV_i/dK_i after the key tile's second step, dQ after the item) by the math warps inside the NEXT step, between
+// its two phases, when the products they wait for have retired anyway.
+// Key tile 0 = frame keys [0,128); key tile 1 = frame keys [128,208) in columns [0,80) + the M global keys in columns
+// [80,96).  Query tile 0 = frame rows [0,128); tile 1 = frame rows [128,196) + global rows at 200..
+// delta_i = sum_d dO_id O_id is precomputed (vip_attn_delta_kernel).  The gradients of the M global rows are emitted as
+// per-frame fp32 partials and reduced by vip_attn_bwd_combine (vip_attention.cu).
+constexpr int TB_MATH_WARPS = 16;
+constexpr int TB_THREADS = (4 + TB_MATH_WARPS) * 32;       // 640
+constexpr int TB_KBUF = (TC_FK + TC_GK) * 128;             // one K' or V' buffer: [208 frame + 16 global rows][128 B]
 constexpr int TB_SQ = 0;                                   // [256][128 B]
 constexpr int TB_SDO = TB_SQ + 256 * 128;                  // [256][128 B]
-constexpr int TB_SK = TB_SDO + 256 * 128;                  // [208][128 B]
-constexpr int TB_SKG = TB_SK + TC_FK * 128;                // [16][128 B]
-constexpr int TB_SV = TB_SKG + TC_GK * 128;
-constexpr int TB_SVG = TB_SV + TC_FK * 128;
-constexpr int TB_SP = TB_SVG + TC_GK * 128;                // [2 atoms][128 rows][128 B]
+constexpr int TB_SK = TB_SDO + 256 * 128;                  // 2 x TB_KBUF
+constexpr int TB_SV = TB_SK + 2 * TB_KBUF;
+constexpr int TB_SP = TB_SV + TB_KBUF;                     // [2 atoms][128 rows][128 B]
 constexpr int TB_SDS = TB_SP + 2 * 128 * 128;
-constexpr int TB_STAT = TB_SDS + 2 * 128 * 128;            // lse*log2e [256] f32, delta [256] f32
-constexpr int TB_BAR = TB_STAT + 2 * 256 * 4;
-constexpr int TB_SMEM = TB_BAR + 128;
+constexpr int TB_BAR = TB_SDS + 2 * 128 * 128;
+constexpr int TB_SMEM = TB_BAR + 256;
+static_assert(TB_KBUF % 1024 == 0 && TB_SMEM + 1024 <= 232448, "shared-memory plan");
+
+enum TbBar { Q0_FULL = 0, Q1_FULL, V0_FULL, V1_FULL, K_FULL, K_FULL1, Q0_FREE, Q1_FREE, V0_FREE, V1_FREE, K_FREE, K_FREE1,
+             S_READY, S_FREE, DP_READY, PDS_READY, G_DONE, TB_NBAR };
+
+struct TbMaps {
+  CUtensorMap qkv_a, qkv_b, qkv_l, qkv_g;   // boxes of 64 columns x {min(L,128), L-128, L, M} rows over qkv [rows, 3C]
+  CUtensorMap do_a, do_b, do_g;             // same row boxes over dO [rows, C]
+};
 
 __global__ void __launch_bounds__(256)
 vip_attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
@@ -379,47 +394,45 @@ vip_attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16
   }
 }
 
+// live-key bit mask of the 32 columns [32 wg, 32 wg + 32) of key tile i (bit e = column 32 wg + e)
+__device__ __forceinline__ uint32_t tb_col_mask(int i, int wg, int L, int M, bool glob_keys_masked) {
+  const int c0 = wg * 32;
+  if (i == 0) {
+    const int n = L - c0;
+    return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+  }
+  const int nf = min(L - 128, 80) - c0;                      // live frame keys from column c0 on
+  uint32_t m = nf >= 32 ? 0xffffffffu : (nf <= 0 ? 0u : ((1u << nf) - 1u));
+  if (!glob_keys_masked) {
+    const int g0 = 80 - c0;                                  // bit of the first global key
+    if (g0 >= 0 && g0 < 32) m |= ((1u << M) - 1u) << g0;     // M <= 8 and 80 % 32 == 16: never crosses the word
+  }
+  return m;
+}
+
 __global__ void __launch_bounds__(TB_THREADS, 1)
-vip_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_f, const __grid_constant__ CUtensorMap tm_qkv_g,
-                       const __grid_constant__ CUtensorMap tm_do_f, const __grid_constant__ CUtensorMap tm_do_g,
-                       const float* __restrict__ lse, const float* __restrict__ delta,
+vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restrict__ lse, const float* __restrict__ delta,
                        __nv_bfloat16* __restrict__ dqkv, float* __restrict__ gpart, const TcDims d, float q_scale) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  float* s_lse = reinterpret_cast<float*>(gbase + TB_STAT);
-  float* s_del = s_lse + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + TB_BAR);
-  uint64_t* full = bars + 0;        // operands of problem n staged (4 producer warps)
-  uint64_t* smem_free = bars + 1;   // every MMA of problem n retired
-  uint64_t* sd_ready = bars + 2;    // S, dP of a step in TMEM
-  uint64_t* pds_ready = bars + 3;   // P, dS of a step in shared memory (256 threads)
-  uint64_t* kv_ready = bars + 4;    // dK_i, dV_i complete
-  uint64_t* kv_free = bars + 5;     // ... and drained (256 threads)
-  uint64_t* q_ready = bars + 6;     // dQ_0, dQ_1 complete
-  uint64_t* q_free = bars + 7;      // ... and drained (256 threads)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(gbase + TB_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + TB_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total = d.B * d.H * d.T;
+  const int L1 = d.L < 128 ? d.L : 128, L2 = d.L - L1;
 
   if (tid == 0) {
-    mbar_init(full, 3);              // TMA expect_tx arrival + the two statistics warps
-    mbar_init(smem_free, 1);
-    mbar_init(sd_ready, 1);
-    mbar_init(pds_ready, 256);
-    mbar_init(kv_ready, 1);
-    mbar_init(kv_free, 256);
-    mbar_init(q_ready, 1);
-    mbar_init(q_free, 256);
+    for (int i = 0; i < TB_NBAR; ++i) mbar_init(&bar[i], (i == S_FREE || i == PDS_READY) ? TB_MATH_WARPS : 1);
     fence_barrier_init();
   }
-  if (warp == 13) {
+  if (warp == 2) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  for (int i = tid; i < TB_STAT / 16; i += TB_THREADS)   // zero all operand tiles once (padding rows stay zero)
+  for (int i = tid; i < TB_BAR / 16; i += TB_THREADS)   // zero all operand tiles once (padding rows stay zero)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 16), "r"(0) : "memory");
   fence_proxy_async_smem();
   tc_fence_before();
@@ -429,42 +442,42 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_f, const __gri
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320,
                  tdQ = tmem_base + 384;
 
-  if (warp == 0 || warp == 12) {
-    // ----------------------------------------------------------------------------------- producers
-    // warp 0 lane 0: eight TMA box loads per problem — the L frame rows and the M global rows of the Q', K', V' head
-    // slices of qkv and of dO — land in the 128B-swizzled tiles the UMMA descriptors read (padding rows stay zero from
-    // the initial clear); warps 0 / 12 also stage lse * log2(e) / delta of the query rows.
-    const int role = warp == 0 ? 0 : 1;
-    int n = 0;
-    for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
-      const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
-      mbar_wait(smem_free, (n & 1) ^ 1);
-      const long long tok_g = static_cast<long long>(b) * d.S, tok_f = tok_g + d.M + static_cast<long long>(t) * d.L;
-      if (role == 0 && lane == 0) {
-        mbar_arrive_expect_tx(full, 4u * static_cast<uint32_t>(d.L + d.M) * 128u);
-        const int rf = static_cast<int>(tok_f), rg = static_cast<int>(tok_g);
+  if (warp == 0) {
+    // ----------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int n = 0;
+      for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
+        const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
+        const int kb = n & 1;
+        const uint32_t pi = n & 1, pk = (n >> 1) & 1;
+        const int rg = static_cast<int>(static_cast<long long>(b) * d.S);
+        const int rf = rg + d.M + t * d.L;
         const int cq = h * TC_HD, ck = d.C + h * TC_HD, cv = 2 * d.C + h * TC_HD;
-        tma_load_2d(gbase + TB_SQ, &tm_qkv_f, full, cq, rf);
-        tma_load_2d(gbase + TB_SQ + TC_GROW * 128, &tm_qkv_g, full, cq, rg);
-        tma_load_2d(gbase + TB_SDO, &tm_do_f, full, cq, rf);
-        tma_load_2d(gbase + TB_SDO + TC_GROW * 128, &tm_do_g, full, cq, rg);
-        tma_load_2d(gbase + TB_SK, &tm_qkv_f, full, ck, rf);
-        tma_load_2d(gbase + TB_SKG, &tm_qkv_g, full, ck, rg);
-        tma_load_2d(gbase + TB_SV, &tm_qkv_f, full, cv, rf);
-        tma_load_2d(gbase + TB_SVG, &tm_qkv_g, full, cv, rg);
-      }
-      {   // per-row statistics of the query rows: lse * log2(e) (+inf on padding rows) / delta
-        const float* src = (role == 0 ? lse : delta) + (static_cast<long long>(b) * d.H + h) * d.S;
-        float* dst = role == 0 ? s_lse : s_del;
-        for (int row = lane; row < 256; row += 32) {
-          float v = role == 0 ? INFINITY : 0.f;
-          if (row < d.L) v = src[d.M + static_cast<long long>(t) * d.L + row] * (role == 0 ? TC_LOG2E : 1.f);
-          else if (row >= TC_GROW && row < TC_GROW + d.M) v = src[row - TC_GROW] * (role == 0 ? TC_LOG2E : 1.f);
-          dst[row] = v;
+        uint8_t* sK = gbase + TB_SK + kb * TB_KBUF;
+        mbar_wait(&bar[K_FREE + kb], pk ^ 1);
+        mbar_arrive_expect_tx(&bar[K_FULL + kb], static_cast<uint32_t>(d.L + d.M) * 128u);
+        tma_load_2d(sK, &tm.qkv_l, &bar[K_FULL + kb], ck, rf);
+        tma_load_2d(sK + TC_FK * 128, &tm.qkv_g, &bar[K_FULL + kb], ck, rg);
+        mbar_wait(&bar[Q0_FREE], pi ^ 1);
+        mbar_arrive_expect_tx(&bar[Q0_FULL], 2u * static_cast<uint32_t>(L1) * 128u);
+        tma_load_2d(gbase + TB_SQ, &tm.qkv_a, &bar[Q0_FULL], cq, rf);
+        tma_load_2d(gbase + TB_SDO, &tm.do_a, &bar[Q0_FULL], cq, rf);
+        mbar_wait(&bar[V0_FREE], pi ^ 1);
+        mbar_arrive_expect_tx(&bar[V0_FULL], static_cast<uint32_t>(L1) * 128u);
+        tma_load_2d(gbase + TB_SV, &tm.qkv_a, &bar[V0_FULL], cv, rf);
+        mbar_wait(&bar[Q1_FREE], pi ^ 1);
+        mbar_arrive_expect_tx(&bar[Q1_FULL], 2u * static_cast<uint32_t>(L2 + d.M) * 128u);
+        if (L2 > 0) {
+          tma_load_2d(gbase + TB_SQ + 128 * 128, &tm.qkv_b, &bar[Q1_FULL], cq, rf + 128);
+          tma_load_2d(gbase + TB_SDO + 128 * 128, &tm.do_b, &bar[Q1_FULL], cq, rf + 128);
         }
+        tma_load_2d(gbase + TB_SQ + TC_GROW * 128, &tm.qkv_g, &bar[Q1_FULL], cq, rg);
+        tma_load_2d(gbase + TB_SDO + TC_GROW * 128, &tm.do_g, &bar[Q1_FULL], cq, rg);
+        mbar_wait(&bar[V1_FREE], pi ^ 1);
+        mbar_arrive_expect_tx(&bar[V1_FULL], static_cast<uint32_t>(L2 + d.M) * 128u);
+        if (L2 > 0) tma_load_2d(gbase + TB_SV + 128 * 128, &tm.qkv_b, &bar[V1_FULL], cv, rf + 128);
+        tma_load_2d(gbase + TB_SV + TC_FK * 128, &tm.qkv_g, &bar[V1_FULL], cv, rg);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full);
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------------- MMA issuer
@@ -474,220 +487,306 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv_f, const __gri
       constexpr uint32_t id_s16 = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t id_kv = make_idesc_bf16(128, TC_HD, 1, 1);   // A = P / dS MN-major, B = dO / Q MN-major
       constexpr uint32_t id_q = make_idesc_bf16(128, TC_HD, 0, 1);    // A = dS K-major, B = K MN-major
-      const uint32_t sQ = base + TB_SQ, sdO = base + TB_SDO, sK = base + TB_SK, sKg = base + TB_SKG, sV = base + TB_SV,
-                     sVg = base + TB_SVG, sP = base + TB_SP, sdS = base + TB_SDS;
+      const uint32_t sQ = base + TB_SQ, sdO = base + TB_SDO, sV = base + TB_SV, sVg = sV + TC_FK * 128,
+                     sP = base + TB_SP, sdS = base + TB_SDS;
+      // the three gradient products of step (i, j) with K' in buffer kb
+      auto issue_grads = [&](int i, int j, int kb) {
+        const uint32_t sK = base + TB_SK + kb * TB_KBUF, sKg = sK + TC_FK * 128;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // K = the 128 query rows of tile j
+          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+          umma_bf16(tdV, make_smem_desc_sw128(sP + ks * 2048, 16384, 1024),
+                    make_smem_desc_sw128(sdO + j * 16384 + ks * 2048, 16384, 1024), id_kv, acc);
+          umma_bf16(tdK, make_smem_desc_sw128(sdS + ks * 2048, 16384, 1024),
+                    make_smem_desc_sw128(sQ + j * 16384 + ks * 2048, 16384, 1024), id_kv, acc);
+        }
+        const uint32_t tq = tdQ + j * 64;
+        if (i == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)   // K = frame keys [0,128): atom ks/4, 32 B per k-step inside it
+            umma_bf16(tq, make_smem_desc_sw128(sdS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(sK + ks * 2048, 16384, 1024), id_q, ks > 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 5; ++ks)   // frame keys [128,208)
+            umma_bf16(tq, make_smem_desc_sw128(sdS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(sK + (128 + ks * 16) * 128, 16384, 1024), id_q, 1u);
+          umma_bf16(tq, make_smem_desc_sw128(sdS + 16384 + 32, 16, 1024),   // columns [80,96): the global keys
+                    make_smem_desc_sw128(sKg, 16384, 1024), id_q, 1u);
+        }
+      };
       int n = 0;
-      uint32_t step = 0, kvt = 0;
+      uint32_t step = 0;
       for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
-        mbar_wait(full, n & 1);
-        fence_proxy_async_smem();
-        for (int i = 0; i < 2; ++i) {
-          for (int j = 0; j < 2; ++j, ++step) {
-            // ---- S = Q_j K_i^T, dP = dO_j V_i^T
-            tc_fence_after();
+        const int kb = n & 1;
+        const uint32_t pi = n & 1, pk = (n >> 1) & 1;
+        const uint32_t sK = base + TB_SK + kb * TB_KBUF, sKg = sK + TC_FK * 128;
+        for (int s = 0; s < 4; ++s, ++step) {
+          const int i = s >> 1, j = s & 1;
+          // ---- S_n = Q_j K_i^T
+          if (s == 0) {
+            mbar_wait(&bar[Q0_FULL], pi);
+            mbar_wait(&bar[K_FULL + kb], pk);
+          } else if (s == 1) {
+            mbar_wait(&bar[Q1_FULL], pi);
+          }
+          if (step > 0) mbar_wait(&bar[S_FREE], (step - 1) & 1);      // phase 1 of the previous step has read its S
+          tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t aq = make_smem_desc_sw128(sQ + j * 16384 + ks * 32, 16, 1024);
-              const uint64_t ao = make_smem_desc_sw128(sdO + j * 16384 + ks * 32, 16, 1024);
-              const uint32_t acc = ks > 0 ? 1u : 0u;
-              if (i == 0) {
-                umma_bf16(tS, aq, make_smem_desc_sw128(sK + ks * 32, 16, 1024), id_s128, acc);
-                umma_bf16(tdP, ao, make_smem_desc_sw128(sV + ks * 32, 16, 1024), id_s128, acc);
-              } else {
-                umma_bf16(tS, aq, make_smem_desc_sw128(sK + 128 * 128 + ks * 32, 16, 1024), id_s80, acc);
-                umma_bf16(tS + 80, aq, make_smem_desc_sw128(sKg + ks * 32, 16, 1024), id_s16, acc);
-                umma_bf16(tdP, ao, make_smem_desc_sw128(sV + 128 * 128 + ks * 32, 16, 1024), id_s80, acc);
-                umma_bf16(tdP + 80, ao, make_smem_desc_sw128(sVg + ks * 32, 16, 1024), id_s16, acc);
-              }
-            }
-            umma_commit(sd_ready);
-            // ---- wait for P, dS of this step, then the three gradient products
-            mbar_wait(pds_ready, step & 1);
-            fence_proxy_async_smem();
-            tc_fence_after();
-            if (j == 0) {
-              mbar_wait(kv_free, (kvt & 1) ^ 1);   // dK_i / dV_i accumulators drained by the previous key tile
-              tc_fence_after();
-            }
-            if (i == 0 && j == 0) {
-              mbar_wait(q_free, (n & 1) ^ 1);
-              tc_fence_after();
-            }
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {   // K = the 128 query rows of tile j
-              const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-              umma_bf16(tdV, make_smem_desc_sw128(sP + ks * 2048, 16384, 1024),
-                        make_smem_desc_sw128(sdO + j * 16384 + ks * 2048, 16384, 1024), id_kv, acc);
-              umma_bf16(tdK, make_smem_desc_sw128(sdS + ks * 2048, 16384, 1024),
-                        make_smem_desc_sw128(sQ + j * 16384 + ks * 2048, 16384, 1024), id_kv, acc);
-            }
-            const uint32_t tq = tdQ + j * 64;
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t aq = make_smem_desc_sw128(sQ + j * 16384 + ks * 32, 16, 1024);
+            const uint32_t acc = ks > 0 ? 1u : 0u;
             if (i == 0) {
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks)   // K = frame keys [0,128): atom ks/4, 32 B per k-step inside it
-                umma_bf16(tq, make_smem_desc_sw128(sdS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                          make_smem_desc_sw128(sK + ks * 2048, 16384, 1024), id_q, ks > 0 ? 1u : 0u);
+              umma_bf16(tS, aq, make_smem_desc_sw128(sK + ks * 32, 16, 1024), id_s128, acc);
             } else {
-#pragma unroll
-              for (int ks = 0; ks < 5; ++ks)   // frame keys [128,208)
-                umma_bf16(tq, make_smem_desc_sw128(sdS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                          make_smem_desc_sw128(sK + (128 + ks * 16) * 128, 16384, 1024), id_q, 1u);
-              umma_bf16(tq, make_smem_desc_sw128(sdS + 16384 + 32, 16, 1024),   // columns [80,96): the global keys
-                        make_smem_desc_sw128(sKg, 16384, 1024), id_q, 1u);
+              umma_bf16(tS, aq, make_smem_desc_sw128(sK + 128 * 128 + ks * 32, 16, 1024), id_s80, acc);
+              umma_bf16(tS + 80, aq, make_smem_desc_sw128(sKg + ks * 32, 16, 1024), id_s16, acc);
             }
-            if (j == 1) {
-              umma_commit(kv_ready);
-              ++kvt;
+          }
+          umma_commit(&bar[S_READY]);
+          // ---- dP_n = dO_j V_i^T
+          if (s == 0) mbar_wait(&bar[V0_FULL], pi);
+          else if (s == 2) mbar_wait(&bar[V1_FULL], pi);
+          if (step > 0) {
+            mbar_wait(&bar[PDS_READY], (step - 1) & 1);               // dP of the previous step consumed; its P, dS staged
+            fence_proxy_async_smem();
+          }
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t ao = make_smem_desc_sw128(sdO + j * 16384 + ks * 32, 16, 1024);
+            const uint32_t acc = ks > 0 ? 1u : 0u;
+            if (i == 0) {
+              umma_bf16(tdP, ao, make_smem_desc_sw128(sV + ks * 32, 16, 1024), id_s128, acc);
+            } else {
+              umma_bf16(tdP, ao, make_smem_desc_sw128(sV + 128 * 128 + ks * 32, 16, 1024), id_s80, acc);
+              umma_bf16(tdP + 80, ao, make_smem_desc_sw128(sVg + ks * 32, 16, 1024), id_s16, acc);
+            }
+          }
+          umma_commit(&bar[DP_READY]);
+          if (s == 1) umma_commit(&bar[V0_FREE]);
+          else if (s == 3) umma_commit(&bar[V1_FREE]);
+          // ---- gradient products of the previous step
+          if (step > 0) {
+            const int ps = (s + 3) & 3, pkb = s == 0 ? (kb ^ 1) : kb;
+            issue_grads(ps >> 1, ps & 1, pkb);
+            umma_commit(&bar[G_DONE]);
+            if (ps == 2) umma_commit(&bar[Q0_FREE]);
+            else if (ps == 3) {
+              umma_commit(&bar[Q1_FREE]);
+              umma_commit(&bar[K_FREE + pkb]);
             }
           }
         }
-        umma_commit(q_ready);
-        umma_commit(smem_free);
+      }
+      if (step > 0) {   // the last step's gradient products
+        mbar_wait(&bar[PDS_READY], (step - 1) & 1);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        issue_grads(1, 1, (n - 1) & 1);
+        umma_commit(&bar[G_DONE]);
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4) {
     // ------------------------------------------------------------------------- math warpgroups
-    const int wg = (warp - 4) >> 2;               // 0: key columns [0,64) / dV / dQ_0;  1: [64,128) / dK / dQ_1
-    const int wq = warp & 3;
-    const int trow = wq * 32 + lane;               // TMEM lane == row of the current tile
+    const int wg = (warp - 4) >> 2;               // key columns [32 wg, 32 wg + 32) of a step
+    const int wq = warp & 3;                       // TMEM lane quarter
+    const int trow = wq * 32 + lane;               // TMEM lane == row of the current query tile
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t sP = base + TB_SP + wg * 16384, sdS = base + TB_SDS + wg * 16384;
-    int n = 0;
-    uint32_t step = 0, kvt = 0;
-    for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
+    const uint32_t sPw = base + TB_SP + (wg >> 1) * 16384, sdSw = base + TB_SDS + (wg >> 1) * 16384;
+    const int chunk0 = (wg & 1) * 4;               // first 16-byte chunk of this warpgroup inside its 64-column atom
+    // rows of the two query tiles this thread owns, and whether its warp has any live row there
+    bool warp_live[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r0 = j * 128 + wq * 32;
+      warp_live[j] = (r0 < d.L) || (r0 + 31 >= TC_GROW && r0 < TC_GROW + d.M);
+    }
+    auto load_stats = [&](int prob, float (&l2)[2], float (&dl)[2]) {
+      const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
+      const long long sb = (static_cast<long long>(b) * d.H + h) * d.S;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int row = j * 128 + trow;
+        long long idx = -1;
+        if (row < d.L) idx = sb + d.M + static_cast<long long>(t) * d.L + row;
+        else if (row >= TC_GROW && row < TC_GROW + d.M) idx = sb + (row - TC_GROW);
+        l2[j] = idx >= 0 ? lse[idx] * TC_LOG2E : INFINITY;     // +inf on padding rows -> P = 0
+        dl[j] = idx >= 0 ? delta[idx] : 0.f;
+      }
+    };
+    // dV_i / dK_i: warpgroups 0,1 drain the two 32-column halves of dV, warpgroups 2,3 those of dK; thread = key row
+    auto drain_kv = [&](int i, int prob) {
       const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
       const long long tok_g = static_cast<long long>(b) * d.S, tok_f = tok_g + d.M + static_cast<long long>(t) * d.L;
-      float* gp = gpart + ((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M * 3 * TC_HD;
-      for (int i = 0; i < 2; ++i) {
-        for (int j = 0; j < 2; ++j, ++step) {
-          const int row = j * 128 + trow;
-          const bool q_glob = row >= TC_GROW && row < TC_GROW + d.M;
-          mbar_wait(sd_ready, step & 1);
-          tc_fence_after();
-          const float l2 = s_lse[row], dl = s_del[row];   // +inf lse on padding rows -> P = 0
+      int key = -1, gk = -1;
+      if (i == 0) { if (trow < d.L) key = trow; }
+      else if (trow < 80) { if (128 + trow < d.L) key = 128 + trow; }
+      else if (trow < 80 + d.M) gk = trow - 80;
+      const int r0 = wq * 32;
+      const bool any = i == 0 ? (r0 < d.L) : (r0 < 80 ? (128 + r0 < d.L) || r0 + 31 >= 80 : r0 < 80 + d.M);
+      if (!any) return;
+      const int which = wg >> 1, half = wg & 1;          // 0: dV, 1: dK
+      uint32_t o[32];
+      tmem_ld32((which == 0 ? tdV : tdK) + lane_off + half * 32, o);
+      tmem_ld_wait(o);
+      const int sect = which == 0 ? 2 : 1;
+      if (key >= 0) {
+        __nv_bfloat16* drow = dqkv + (tok_f + key) * d.ld_qkv + sect * d.C + h * TC_HD + half * 32;
 #pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {                 // 32 key columns per TMEM load pair
-            uint32_t rs32[32], rp32[32];
-            tmem_ld32(tS + lane_off + wg * 64 + c2 * 32, rs32);
-            tmem_ld32(tdP + lane_off + wg * 64 + c2 * 32, rp32);
-            tmem_ld_wait(rs32);
-            tmem_ld_wait(rp32);
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]), __uint_as_float(o[q * 8 + 1]));
+          v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3]));
+          v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5]));
+          v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7]));
+          *reinterpret_cast<uint4*>(drow + q * 8) = v;
+        }
+      } else if (gk >= 0) {
+        float* grow = gpart + (((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M + gk) * 3 * TC_HD + sect * TC_HD + half * 32;
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {                 // 16 key columns = two 16-byte chunks of P and of dS
-            const int c = c2 * 2 + ch;
-            const int col0 = wg * 64 + c * 16;
-            const uint32_t* rs = rs32 + ch * 16;
-            const uint32_t* rp = rp32 + ch * 16;
-            uint32_t pk[8], dk[8];
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(grow + q * 4) = make_float4(__uint_as_float(o[q * 4]), __uint_as_float(o[q * 4 + 1]),
+                                                                 __uint_as_float(o[q * 4 + 2]), __uint_as_float(o[q * 4 + 3]));
+      }
+    };
+    // dQ_0 (warpgroups 0,1) / dQ_1 (warpgroups 2,3), 32 columns each; thread = query row
+    auto drain_q = [&](int prob) {
+      const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
+      const long long tok_g = static_cast<long long>(b) * d.S, tok_f = tok_g + d.M + static_cast<long long>(t) * d.L;
+      const int j = wg >> 1, half = wg & 1;
+      if (!warp_live[j]) return;
+      const int row = j * 128 + trow;
+      uint32_t o[32];
+      tmem_ld32(tdQ + j * 64 + half * 32 + lane_off, o);
+      tmem_ld_wait(o);
+      if (row < d.L) {
+        __nv_bfloat16* drow = dqkv + (tok_f + row) * d.ld_qkv + h * TC_HD + half * 32;
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              float pv[2], dv[2];
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * q_scale, __uint_as_float(o[q * 8 + 1]) * q_scale);
+          v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * q_scale, __uint_as_float(o[q * 8 + 3]) * q_scale);
+          v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * q_scale, __uint_as_float(o[q * 8 + 5]) * q_scale);
+          v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * q_scale, __uint_as_float(o[q * 8 + 7]) * q_scale);
+          *reinterpret_cast<uint4*>(drow + q * 8) = v;
+        }
+      } else if (row >= TC_GROW && row < TC_GROW + d.M) {
+        float* grow = gpart + (((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M + (row - TC_GROW)) * 3 * TC_HD + half * 32;
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int col = col0 + e + u;
-                bool live;
-                if (i == 0) live = col < d.L;
-                else live = col < 80 ? (128 + col < d.L) : (col < 96 && (col - 80) < d.M && !(q_glob && t != 0));
-                // dead columns may hold stale TMEM bits (even NaN): select, never multiply by them
-                const float p = live ? tc_exp2(fmaf(__uint_as_float(rs[e + u]), TC_LOG2E, -l2)) : 0.f;
-                pv[u] = p;
-                dv[u] = live ? p * (__uint_as_float(rp[e + u]) - dl) : 0.f;
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(grow + q * 4) = make_float4(__uint_as_float(o[q * 4]), __uint_as_float(o[q * 4 + 1]),
+                                                                 __uint_as_float(o[q * 4 + 2]), __uint_as_float(o[q * 4 + 3]));
+      }
+    };
+
+    float l2n[2], dln[2];
+    if (static_cast<int>(blockIdx.x) < total) load_stats(blockIdx.x, l2n, dln);
+    uint32_t step = 0;
+    int prev_prob = -1;
+    for (int prob = blockIdx.x; prob < total; prob += gridDim.x) {
+      const int t = prob % d.T;
+      const float l2[2] = {l2n[0], l2n[1]}, dl[2] = {dln[0], dln[1]};
+      if (prob + static_cast<int>(gridDim.x) < total) load_stats(prob + gridDim.x, l2n, dln);   // prefetch the next item's rows
+      for (int s = 0; s < 4; ++s, ++step) {
+        const int i = s >> 1, j = s & 1;
+        const int row = j * 128 + trow;
+        const bool q_glob = row >= TC_GROW && row < TC_GROW + d.M;
+        const bool cols_on = i == 0 ? (wg * 32 < d.L) : (wg < 3);
+        const bool active = warp_live[j] && cols_on;
+        const uint32_t mask = tb_col_mask(i, wg, d.L, d.M, q_glob && t != 0);
+        // ---- phase 1: P = exp(S - lse) -> packed bf16 in registers
+        uint32_t ppk[16];
+        mbar_wait(&bar[S_READY], step & 1);
+        tc_fence_after();
+        if (active) {
+          uint32_t r[2][16];
+          tmem_ld16(tS + lane_off + wg * 32, r[0]);
+          tmem_ld16(tS + lane_off + wg * 32 + 16, r[1]);
+          tmem_ld_wait16(r[0]);
+          tmem_ld_wait16(r[1]);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[S_FREE]);     // S is in registers: the tensor pipe may overwrite it
+          const float nl = -l2[j];
+          if (mask == 0xffffffffu) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int e = 0; e < 16; e += 2)
+                ppk[c * 8 + (e >> 1)] = pack_bf16(tc_exp2(fmaf(__uint_as_float(r[c][e]), TC_LOG2E, nl)),
+                                                  tc_exp2(fmaf(__uint_as_float(r[c][e + 1]), TC_LOG2E, nl)));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) {
+                const float p0 = (mask >> (c * 16 + e)) & 1u ? tc_exp2(fmaf(__uint_as_float(r[c][e]), TC_LOG2E, nl)) : 0.f;
+                const float p1 = (mask >> (c * 16 + e + 1)) & 1u ? tc_exp2(fmaf(__uint_as_float(r[c][e + 1]), TC_LOG2E, nl)) : 0.f;
+                ppk[c * 8 + (e >> 1)] = pack_bf16(p0, p1);
               }
-              pk[e >> 1] = pack_bf16(pv[0], pv[1]);
-              dk[e >> 1] = pack_bf16(dv[0], dv[1]);
-            }
-            // row `trow`, 16-byte chunks 2c and 2c+1 of this warpgroup's 64-column atom
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sP, trow, 2 * c)), "r"(pk[0]), "r"(pk[1]),
-                         "r"(pk[2]), "r"(pk[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sP, trow, 2 * c + 1)), "r"(pk[4]),
-                         "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdS, trow, 2 * c)), "r"(dk[0]), "r"(dk[1]),
-                         "r"(dk[2]), "r"(dk[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdS, trow, 2 * c + 1)), "r"(dk[4]),
-                         "r"(dk[5]), "r"(dk[6]), "r"(dk[7]) : "memory");
           }
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[S_FREE]);
+        }
+        // ---- the previous step's gradient products have retired: its P / dS tiles are free, its accumulators final
+        if (step > 0) {
+          mbar_wait(&bar[G_DONE], (step - 1) & 1);
+          tc_fence_after();
+          if (s == 2) drain_kv(0, prob);
+          else if (s == 0) {
+            drain_kv(1, prev_prob);
+            drain_q(prev_prob);
+          }
+        }
+        // ---- phase 2: dS = P * (dP - delta); stage P and dS for the gradient products
+        mbar_wait(&bar[DP_READY], step & 1);
+        tc_fence_after();
+        if (active) {
+          uint32_t r[2][16];
+          tmem_ld16(tdP + lane_off + wg * 32, r[0]);
+          tmem_ld16(tdP + lane_off + wg * 32 + 16, r[1]);
+          tmem_ld_wait16(r[0]);
+          tmem_ld_wait16(r[1]);
+          const float dlj = dl[j];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t dk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t pw = ppk[c * 8 + e];
+              dk[e] = pack_bf16(bf16_lo(pw) * (__uint_as_float(r[c][2 * e]) - dlj),
+                                bf16_hi(pw) * (__uint_as_float(r[c][2 * e + 1]) - dlj));
+            }
+            const int ch = chunk0 + c * 2;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sPw, trow, ch)), "r"(ppk[c * 8 + 0]),
+                         "r"(ppk[c * 8 + 1]), "r"(ppk[c * 8 + 2]), "r"(ppk[c * 8 + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sPw, trow, ch + 1)), "r"(ppk[c * 8 + 4]),
+                         "r"(ppk[c * 8 + 5]), "r"(ppk[c * 8 + 6]), "r"(ppk[c * 8 + 7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdSw, trow, ch)), "r"(dk[0]), "r"(dk[1]),
+                         "r"(dk[2]), "r"(dk[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdSw, trow, ch + 1)), "r"(dk[4]), "r"(dk[5]),
+                         "r"(dk[6]), "r"(dk[7]) : "memory");
           }
           fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(pds_ready);
-          if (j == 1) {
-            // ---- dV_i (WG A) / dK_i (WG B): thread = key row of key tile i
-            mbar_wait(kv_ready, kvt & 1);
-            ++kvt;
-            tc_fence_after();
-            int key = -1, gk = -1;
-            if (i == 0) { if (trow < d.L) key = trow; }
-            else if (trow < 80) { if (128 + trow < d.L) key = 128 + trow; }
-            else if (trow < 80 + d.M) gk = trow - 80;
-            const uint32_t tsrc = (wg == 0 ? tdV : tdK) + lane_off;
-            __nv_bfloat16* drow = dqkv + (tok_f + key) * d.ld_qkv + (wg == 0 ? 2 : 1) * d.C + h * TC_HD;
-            float* grow = gp + static_cast<long long>(gk) * 3 * TC_HD + (wg == 0 ? 2 : 1) * TC_HD;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t o[32];
-              tmem_ld32(tsrc + half * 32, o);
-              tmem_ld_wait(o);
-              if (half == 1) {
-                tc_fence_before();
-                mbar_arrive(kv_free);
-              }
-              if (key >= 0) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  uint4 v;
-                  v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]), __uint_as_float(o[q * 8 + 1]));
-                  v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3]));
-                  v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5]));
-                  v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7]));
-                  *reinterpret_cast<uint4*>(drow + half * 32 + q * 8) = v;
-                }
-              } else if (gk >= 0) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) grow[half * 32 + e] = __uint_as_float(o[e]);
-              }
-            }
-          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[PDS_READY]);
       }
-      // ---- dQ_0 (WG A) / dQ_1 (WG B): thread = query row
-      {
-        mbar_wait(q_ready, n & 1);
-        tc_fence_after();
-        const int row = wg * 128 + trow;
-        const bool is_frame = row < d.L;
-        const int gq = (row >= TC_GROW && row < TC_GROW + d.M) ? row - TC_GROW : -1;
-        __nv_bfloat16* drow = dqkv + (tok_f + row) * d.ld_qkv + h * TC_HD;
-        float* grow = gp + static_cast<long long>(gq) * 3 * TC_HD;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t o[32];
-          tmem_ld32(tdQ + wg * 64 + lane_off + half * 32, o);
-          tmem_ld_wait(o);
-          if (half == 1) {
-            tc_fence_before();
-            mbar_arrive(q_free);
-          }
-          if (is_frame) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 v;
-              v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * q_scale, __uint_as_float(o[q * 8 + 1]) * q_scale);
-              v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * q_scale, __uint_as_float(o[q * 8 + 3]) * q_scale);
-              v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * q_scale, __uint_as_float(o[q * 8 + 5]) * q_scale);
-              v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * q_scale, __uint_as_float(o[q * 8 + 7]) * q_scale);
-              *reinterpret_cast<uint4*>(drow + half * 32 + q * 8) = v;
-            }
-          } else if (gq >= 0) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) grow[half * 32 + e] = __uint_as_float(o[e]);
-          }
-        }
-      }
+      prev_prob = prob;
+    }
+    if (step > 0) {   // accumulators of the last item
+      mbar_wait(&bar[G_DONE], (step - 1) & 1);
+      tc_fence_after();
+      drain_kv(1, prev_prob);
+      drain_q(prev_prob);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -709,6 +808,7 @@ extern "C" int xp_vip_attention_bwd_tc_partial(const void* qkv, const void* out,
   d.ld_o = C;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long rows = static_cast<long long>(B) * d.S;
+  if (rows >= (1LL << 31)) return fail("vip_attention: more than 2^31 token rows");
   vip_attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, rows, d.S, C, H);
   XP_CHECK_LAUNCH("vip_attn_delta_kernel");
@@ -720,14 +820,18 @@ extern "C" int xp_vip_attention_bwd_tc_partial(const void* qkv, const void* out,
   }
   const long long total = static_cast<long long>(B) * H * T;
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
-  // TMA boxes: 64 columns (one head slice) x L frame rows / x M global rows of the token-major buffers
-  CUtensorMap tm_qkv_f, tm_qkv_g, tm_do_f, tm_do_g;
-  if (make_tmap_bf16_2d(&tm_qkv_f, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, L)) return -1;
-  if (make_tmap_bf16_2d(&tm_qkv_g, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, M)) return -1;
-  if (make_tmap_bf16_2d(&tm_do_f, dout, C, rows, d.ld_o, TC_HD, L)) return -1;
-  if (make_tmap_bf16_2d(&tm_do_g, dout, C, rows, d.ld_o, TC_HD, M)) return -1;
-  vip_attn_bwd_tc_kernel<<<grid, TB_THREADS, smem, st>>>(
-      tm_qkv_f, tm_qkv_g, tm_do_f, tm_do_g, lse, delta, static_cast<__nv_bfloat16*>(dqkv), workspace, d, q_scale);
+  // TMA boxes: 64 columns (one head slice) x {first 128, remaining, all L, M global} rows of the token-major buffers
+  const int L1 = L < 128 ? L : 128, L2 = L - L1;
+  TbMaps tm;
+  if (make_tmap_bf16_2d(&tm.qkv_a, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, L1)) return -1;
+  if (make_tmap_bf16_2d(&tm.qkv_b, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, L2 > 0 ? L2 : 1)) return -1;
+  if (make_tmap_bf16_2d(&tm.qkv_l, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, L)) return -1;
+  if (make_tmap_bf16_2d(&tm.qkv_g, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, M)) return -1;
+  if (make_tmap_bf16_2d(&tm.do_a, dout, C, rows, d.ld_o, TC_HD, L1)) return -1;
+  if (make_tmap_bf16_2d(&tm.do_b, dout, C, rows, d.ld_o, TC_HD, L2 > 0 ? L2 : 1)) return -1;
+  if (make_tmap_bf16_2d(&tm.do_g, dout, C, rows, d.ld_o, TC_HD, M)) return -1;
+  vip_attn_bwd_tc_kernel<<<grid, TB_THREADS, smem, st>>>(tm, lse, delta, static_cast<__nv_bfloat16*>(dqkv), workspace, d,
+                                                         q_scale);
   XP_CHECK_LAUNCH("vip_attn_bwd_tc_kernel");
   return 0;
 }

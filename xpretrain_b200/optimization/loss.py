@@ -22,8 +22,12 @@ def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
-def _nce_forward(vis: torch.Tensor, txt: torch.Tensor, temp: torch.Tensor):
-    """vis, txt: [N, d] fp32 (gathered).  Returns (loss[1], g_scaled[N, Np] bf16, vis_hi, txt_hi, dscale[1])."""
+FUSED_MAX_N = 1536      # (N / 128)^2 tiles of the fused kernel must be co-resident on the 148 SMs
+
+
+def _nce_forward_unfused(vis: torch.Tensor, txt: torch.Tensor, temp: torch.Tensor):
+    """Global batches above FUSED_MAX_N: split / tcgen05 GEMM / softmax-grad as separate launches.
+    vis, txt: [N, d] fp32 (gathered).  Returns (loss[1], g_scaled[N, Np] bf16, vis_hi, txt_hi, dscale[1])."""
     N, d = vis.shape
     Np = _pad8(N)
     dev = vis.device
@@ -42,6 +46,97 @@ def _nce_forward(vis: torch.Tensor, txt: torch.Tensor, temp: torch.Tensor):
     dscale = torch.zeros(1, dtype=f32, device=dev)
     ops.nce_softmax_grad(z, temp.detach().reshape(1).to(f32), lse_r, lse_c, g, loss, dscale)
     return loss, g, vh, th, dscale
+
+
+class _Exchange:
+    """Per (process group, b, d, device) state of the fused exchange: this rank's exchange buffer in SYMMETRIC MEMORY
+    (torch.distributed._symmetric_memory: cuMem allocation mapped by every peer over NVLink), the device array of all
+    ranks' base pointers, the kernel's zeroed workspace and the epoch counter.  world == 1 needs none of it."""
+
+    _cache = {}
+
+    def __init__(self, group, world: int, rank: int, b: int, d: int, dev: torch.device):
+        import torch.distributed as dist
+        self.world, self.rank, self.epoch = world, rank, 0
+        nbytes = int(_lib.lib().xp_nce_gather_exchange_bytes(b, d, world))
+        self.mode = 0
+        try:
+            import torch.distributed._symmetric_memory as symm
+            self.buf = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.buf.zero_()
+            self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(x) for x in self.handle.buffer_ptrs]
+            torch.cuda.synchronize(dev)
+            self.handle.barrier()                     # every rank's flags are zero before anyone raises one
+        except Exception as e:  # noqa: BLE001 — no P2P mapping on this machine: NCCL carries the rows, the kernel still fuses the rest
+            import warnings
+            warnings.warn(f"xpretrain_b200: symmetric-memory rendezvous failed ({type(e).__name__}: {e}); the embedding exchange "
+                          f"falls back to ncclAllGather + the fused kernel in pre-gathered mode")
+            self.mode = 1
+            self.gathered = torch.empty(world, 2, b, d, dtype=f32, device=dev)
+            ptrs = [self.gathered[r, 0].data_ptr() for r in range(world)] + [self.gathered[r, 1].data_ptr() for r in range(world)]
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.ws = torch.zeros(int(_lib.lib().xp_nce_gather_workspace_bytes(world * b)) // 4, dtype=f32, device=dev)
+
+    @classmethod
+    def get(cls, group, world, rank, b, d, dev):
+        key = (id(group) if group is not None else 0, world, rank, b, d, dev)
+        ex = cls._cache.get(key)
+        if ex is None:
+            ex = cls._cache[key] = cls(group, world, rank, b, d, dev)
+        return ex
+
+
+_local_ws = {}
+
+
+def _nce_forward_fused(vis: torch.Tensor, txt: torch.Tensor, temp: torch.Tensor, exchange: "_Exchange" = None, group=None):
+    """One launch of csrc/nce_fused.cu.  vis, txt: this rank's [b, d] fp32 rows.  Returns (loss[1], g_scaled[N, Np] bf16,
+    vis_hi[N, d], txt_hi[N, d], dscale[1]) for the global batch N = world * b."""
+    b, d = vis.shape
+    dev = vis.device
+    world = exchange.world if exchange is not None else 1
+    N = world * b
+    Np = _pad8(N)
+    vis, txt = vis.contiguous(), txt.contiguous()
+    g = (torch.zeros if Np != N else torch.empty)(N, Np, dtype=bf16, device=dev)
+    vh = torch.empty(N, d, dtype=bf16, device=dev)
+    th = torch.empty(N, d, dtype=bf16, device=dev)
+    loss = torch.empty(1, dtype=f32, device=dev)
+    dscale = torch.empty(1, dtype=f32, device=dev)
+    scale = temp.detach().reshape(1).to(f32)
+    a = _lib.XpNceGather()
+    a.vis_local, a.txt_local = vis.data_ptr(), txt.data_ptr()
+    a.logit_scale, a.g_scaled, a.vis_hi, a.txt_hi = scale.data_ptr(), g.data_ptr(), vh.data_ptr(), th.data_ptr()
+    a.loss, a.d_logit_scale = loss.data_ptr(), dscale.data_ptr()
+    a.b, a.d, a.ld_g = b, d, Np
+    keep = None
+    if exchange is None:                                  # single process: rows are read in place
+        key = (N, dev)
+        ws = _local_ws.get(key)
+        if ws is None:
+            ws = _local_ws[key] = (torch.zeros(int(_lib.lib().xp_nce_gather_workspace_bytes(N)) // 4, dtype=f32, device=dev),
+                                   torch.empty(2, dtype=torch.int64, device=dev))
+        keep = torch.tensor([vis.data_ptr(), txt.data_ptr()], dtype=torch.int64).pin_memory()
+        ws[1].copy_(keep, non_blocking=True)
+        a.rank, a.world, a.mode, a.epoch = 0, 1, 1, 0
+        a.peer_bufs, a.workspace = ws[1].data_ptr(), ws[0].data_ptr()
+    else:
+        if exchange.mode == 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(exchange.gathered, torch.stack([vis, txt]), group=group)
+        exchange.epoch += 1
+        a.rank, a.world, a.mode, a.epoch = exchange.rank, world, exchange.mode, exchange.epoch
+        a.peer_bufs, a.workspace = exchange.ptrs.data_ptr(), exchange.ws.data_ptr()
+    ops.check(_lib.lib().xp_nce_gather_fused(ops.C.byref(a), ops._stream()), "xp_nce_gather_fused")
+    return loss, g, vh, th, dscale
+
+
+def _nce_forward(vis: torch.Tensor, txt: torch.Tensor, temp: torch.Tensor):
+    """vis, txt: [N, d] fp32 of ONE process (already gathered, or world == 1)."""
+    if vis.shape[0] <= FUSED_MAX_N and vis.shape[1] % 64 == 0:
+        return _nce_forward_fused(vis, txt, temp)
+    return _nce_forward_unfused(vis, txt, temp)
 
 
 def _nce_backward(g, vh, th, row0: int, nrows: int, scale: float):
@@ -94,7 +189,8 @@ class NCELearnableTempLoss(nn.Module):
 class _GatherNceFunction(torch.autograd.Function):
     """allgather(vis), allgather(txt) -> loss, as one autograd node (run_pretrain.py:344-356).
 
-    Forward: ONE all-gather of the packed [2, b, d] local embeddings (NCCL over NVLink), then the loss.
+    Forward: ONE cooperative kernel (csrc/nce_fused.cu) — device-side flag barrier over symmetric memory, logits tiles
+    whose operands are read straight from the peers' memory over NVLink, softmaxes, loss and dL/dZ.  No NCCL call.
     Backward: every rank already holds all embeddings and computes the same scalar loss, so the local rows of
     dV / dT are produced locally — no backward collective.  `grad_scale` = world size reproduces
     all_reduce(SUM)-then-slice (LF-VILA/src/utils/dist.py:35-41), which a gradient-AVERAGING data-parallel
@@ -107,15 +203,17 @@ class _GatherNceFunction(torch.autograd.Function):
         b, d = vis.shape
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         rank = dist.get_rank(group) if world > 1 else 0
-        if world > 1:
+        if world > 1 and world * b <= FUSED_MAX_N and d % 64 == 0 and (b * d) % 4 == 0:
+            ex = _Exchange.get(group, world, rank, b, d, vis.device)
+            loss, g, vh, th, dscale = _nce_forward_fused(vis.to(f32), txt.to(f32), temp, ex, group)
+        elif world > 1:                                  # global batch beyond one wave of tiles: NCCL gather + separate launches
             local = torch.stack([vis.to(f32), txt.to(f32)]).contiguous()          # [2, b, d]
             gathered = torch.empty(world, 2, b, d, dtype=f32, device=vis.device)
             dist.all_gather_into_tensor(gathered, local, group=group)
-            V = gathered[:, 0].reshape(world * b, d)
-            T = gathered[:, 1].reshape(world * b, d)
+            loss, g, vh, th, dscale = _nce_forward(gathered[:, 0].reshape(world * b, d).contiguous(),
+                                                   gathered[:, 1].reshape(world * b, d).contiguous(), temp)
         else:
-            V, T = vis.to(f32), txt.to(f32)
-        loss, g, vh, th, dscale = _nce_forward(V.contiguous(), T.contiguous(), temp)
+            loss, g, vh, th, dscale = _nce_forward(vis.to(f32).contiguous(), txt.to(f32).contiguous(), temp)
         ctx.saved = (g, vh, th, dscale)
         ctx.meta = (rank * b, b, float(world if grad_scale is None else grad_scale), vis.dtype, txt.dtype, temp.dtype,
                     temp.shape)
