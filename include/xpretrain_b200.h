@@ -109,6 +109,13 @@ enum { XP_DTYPE_F32 = 0, XP_DTYPE_BF16 = 1, XP_DTYPE_F16 = 2 };
  * video [frames,3,H,W] -> patches bf16 [frames*(H/p)*(W/p), 3*p*p]; the conv itself then runs as xp_gemm. */
 int xp_vip_patchify(const void* video, int32_t dtype, void* patches_bf16, int64_t frames, int32_t H, int32_t W,
                     int32_t patch, void* stream);
+/* The reference's input transform fused into the patch extraction: frames_hwc uint8 [frames, H, W, 3] as
+ * the decoder delivers them -> `.permute(0,3,1,2).float() / 255.` (CLIP-ViP/src/datasets/dataset_pretrain_stage1_all_source.py:182)
+ * -> Normalize(mean, std) (init_transform_dict_simple, CLIP-ViP/src/datasets/dataloader.py:209-233; Resize / CenterCrop are
+ * the identity at the input resolution) -> the bf16 patch matrix of xp_vip_patchify.  IEEE fp32 arithmetic, one rounding to
+ * bf16: bit-identical to casting the reference's fp32 tensor.  mean3 / std3 are HOST arrays of 3 floats. */
+int xp_vip_patchify_u8(const uint8_t* frames_hwc, void* patches_bf16, int64_t frames, int32_t H, int32_t W, int32_t patch,
+                       const float* mean3, const float* std3, void* stream);
 /* CLIP_ViP.py:170-176,183-195: table[t*L+l] = interp(temporal_embedding)[t] + position_embedding[1+l] (bf16,
  * [T*L, C]) and the M = 1 + add_cls_num global rows x[b, m] = (class_embedding | added_cls[m-1]) + position_embedding[0]
  * written into x_bf16 [B, M+T*L, C].  temporal may be NULL (if_use_temporal_embed = 0). */

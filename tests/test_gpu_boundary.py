@@ -39,7 +39,6 @@ def test_single_tower_entry_points_against_oracle(dev):
     O, cfg, sd, model = _small(dev)
     video, ids, mask = O.synthetic_batch(3, 2, 16, cfg, seed=8, ragged_text=True)
     want = O.clip_vip_forward(sd, video, ids, mask, cfg)
-    vproj, _ = O.vision_tower(sd, video, cfg), None
     with torch.no_grad():
         fv = model.forward_video(video.to(dev))
         ft = model.forward_text(ids.to(dev), mask.to(dev))
@@ -50,8 +49,8 @@ def test_single_tower_entry_points_against_oracle(dev):
     assert torch.equal(fv, both["vis_features"]) and torch.equal(ft, both["text_features"]) and torch.equal(gi_n, fv)
     assert _rel(fv.cpu(), want["vis_features"]) < 1e-2 and _rel(ft.cpu(), want["text_features"]) < 1e-2
     # un-normalised projections (CLIP_ViP.py:1039-1041, 1083-1085): the oracle towers return them before l2_normalize
-    vis_raw = O.vision_tower(sd, video, cfg)
-    txt_raw = O.text_tower(sd, ids, mask, cfg)
+    vis_raw = O.vision_tower(sd, video, cfg) @ sd["visual_projection.weight"].t()
+    txt_raw = O.text_tower(sd, ids, mask, cfg) @ sd["text_projection.weight"].t()
     assert _rel(gi_raw.cpu(), vis_raw) < 1e-2 and _rel(gt_raw.cpu(), txt_raw) < 1e-2
     assert float((gi_raw.norm(dim=-1) - 1).abs().min()) > 1e-3          # really not normalised
     assert _rel(torch.nn.functional.normalize(gi_raw, dim=-1).cpu(), fv.cpu()) < 1e-5
@@ -77,12 +76,12 @@ def test_freeze_text_encoder(dev):
     for n, g in g1.items():
         if n.startswith("text_model."):
             assert g is None, n
-        else:
-            assert g is not None and torch.equal(g, g0[n]), n            # vision / projections / logit_scale intact
+        else:      # vision / projections / logit_scale intact (fp32 atomics in split-K wgrads: equal to round-off, not bitwise)
+            assert g is not None and float((g - g0[n]).norm()) <= 1e-4 * float(g0[n].norm()) + 1e-12, n
     model.freeze_text_encoder(freeze_text_proj=True)
     _, g2 = run()
     assert g2["text_projection.weight"] is None and all(g is None for n, g in g2.items() if n.startswith("text_model."))
-    assert torch.equal(g2["visual_projection.weight"], g0["visual_projection.weight"])
+    assert _rel(g2["visual_projection.weight"], g0["visual_projection.weight"]) < 1e-4
 
 
 def test_inplace_data_updates_of_the_reference_adamw_reach_the_next_forward(dev):
@@ -116,7 +115,7 @@ def test_inplace_data_updates_of_the_reference_adamw_reach_the_next_forward(dev)
 
 def test_evaluation_forward_keeps_no_activations(dev):
     """under no_grad the autograd.Function must not save the per-layer activations."""
-    O, cfg, sd, model = _small(dev, seed=7, layers=2)
+    O, cfg, sd, model = _small(dev, seed=7, layers=6)
     video, ids, mask = O.synthetic_batch(4, 4, 16, cfg, seed=11)
     video, ids, mask = video.to(dev), ids.to(dev), mask.to(dev)
     def peak(grad):
@@ -129,7 +128,7 @@ def test_evaluation_forward_keeps_no_activations(dev):
     p_eval, _ = peak(False)
     p_train, _ = peak(True)
     print(f"peak forward memory: eval {p_eval / 2**20:.1f} MiB, train {p_train / 2**20:.1f} MiB")
-    assert p_eval < 0.6 * p_train
+    assert p_eval < 0.5 * p_train          # 6 layers of saved activations vs one layer's transients
 
 
 def test_text_length_and_token_id_validation(dev):

@@ -1,5 +1,6 @@
 """B200: every C-ABI kernel against a plain fp32 PyTorch statement of the same op on the same (bf16-rounded) inputs."""
 import math
+import os
 
 import pytest
 import torch
@@ -164,6 +165,38 @@ def test_l2norm_colsum_cast(dev):
 
 
 # ------------------------------------------------------------------------------------------ embeddings
+def test_uint8_frames_preprocessing_bit_exact_vs_reference_transform(dev):
+    """decoder frames uint8 [B, T, H, W, 3] -> the reference's `.permute(0,3,1,2).float() / 255.`
+    (dataset_pretrain_stage1_all_source.py:182) + torchvision Normalize(mean, std) (dataloader.py:209-233; Resize / CenterCrop to
+    the same 224 x 224 are the identity) -> im2col.  Integer input, IEEE fp32 arithmetic, one rounding: bit-exact."""
+    from xpretrain_b200 import ops
+    B, T, H, W = 2, 3, 224, 224
+    g = torch.Generator().manual_seed(12)
+    frames = torch.randint(0, 256, (B, T, H, W, 3), dtype=torch.uint8, generator=g)
+    frames[0, 0, :2] = 255
+    frames[0, 0, 2:4] = 0
+    mean = torch.tensor(ops.CLIP_MEAN, dtype=torch.float32)
+    std = torch.tensor(ops.CLIP_STD, dtype=torch.float32)
+    img = frames.reshape(B * T, H, W, 3).permute(0, 3, 1, 2).float() / 255.                   # reference line 182
+    img = img.clone().sub_(mean[:, None, None]).div_(std[:, None, None])                      # torchvision F.normalize
+    ref_p = img.reshape(B * T, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(B * T * 196, 768).to(bf16)
+    patches = torch.empty(B * T * 196, 768, dtype=bf16, device=dev)
+    ops.vip_patchify_u8(frames.to(dev), patches, 16)
+    assert torch.equal(patches.cpu(), ref_p)
+    # and the model accepts the raw frames: same features as feeding the reference-transformed float video
+    from types import SimpleNamespace
+    from xpretrain_b200.modeling import VidCLIP
+    from xpretrain_b200.modeling.clip_vip import ClipVipConfig, TowerConfig
+    add = SimpleNamespace(type="ViP", temporal_size=12, if_use_temporal_embed=1, logit_scale_init_value=4.6, add_cls_num=3)
+    mc = ClipVipConfig(vision=TowerConfig(768, 12, 1, 3072), text=TowerConfig(512, 8, 1, 2048))
+    torch.manual_seed(0)
+    model = VidCLIP(SimpleNamespace(clip_config=mc, clip_weights="", clip_vision_additional_config=add)).to(dev)
+    with torch.no_grad():
+        a = model.forward_video(frames.to(dev))
+        b = model.forward_video(img.reshape(B, T, 3, H, W).to(dev))
+    assert torch.equal(a, b)
+
+
 def test_patchify_and_embed_tables(dev):
     from oracle import clipvip_oracle as O
     from xpretrain_b200 import ops

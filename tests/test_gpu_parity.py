@@ -204,6 +204,7 @@ def test_hidden_states_against_oracle(dev):
     video, ids, mask = O.synthetic_batch(2, 3, 16, cfg, seed=5, ragged_text=True)
     _, vh = O.vision_tower(sd, video, cfg, return_hidden=True)
     model = _build(cfg, sd, dev)
+    M._refresh_weights(model.clipmodel)
     proj, sv = M._vision_fwd(model.clipmodel, video.to(dev), save=True)
     S = sv.S
     for i, want in enumerate(vh[:-1]):

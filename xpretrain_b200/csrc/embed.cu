@@ -82,6 +82,44 @@ patchify_kernel(const T* __restrict__ video, __nv_bfloat16* __restrict__ out, lo
   *reinterpret_cast<uint4*>(out + row * (3 * p * p) + c * p * p + kh * p + kw) = pack8f(v);
 }
 
+// uint8 frames as the decoder delivers them, [frames, H, W, 3] (HWC), to the same bf16 patch matrix, with the reference's
+// input transform applied on the fly: `img_array.permute(0, 3, 1, 2).float() / 255.` (dataset_pretrain_stage1_all_source.py:182)
+// followed by torchvision Normalize(mean, std) of init_transform_dict_simple (dataloader.py:209-233) for frames that already
+// have the input resolution (Resize / CenterCrop to the same size are the identity).  IEEE division / subtraction in fp32
+// (explicit _rn intrinsics: the library is built with --use_fast_math), then ONE rounding to bf16 — bit-identical to
+// casting the reference's fp32 tensor.  A step then uploads 1 byte per sample value instead of 4.
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __restrict__ out, long long n_frames, int H, int W, int p,
+                   float m0, float m1, float m2, float s0, float s1, float s2) {
+  // one thread per 8 consecutive pixels of an image row (24 contiguous bytes); p % 8 == 0, W % 8 == 0
+  const int wchunks = W / 8;
+  const long long total = n_frames * H * wchunks;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wc = static_cast<int>(idx % wchunks);
+  long long rest = idx / wchunks;
+  const int y = static_cast<int>(rest % H);
+  const long long f = rest / H;
+  const uint2* src = reinterpret_cast<const uint2*>(frames + ((f * H + y) * W + wc * 8) * 3);
+  const uint2 a = src[0], b = src[1], c = src[2];
+  const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+  const int gw = W / p, gh = H / p;
+  const int pw = (wc * 8) / p, kw = (wc * 8) % p, ph = y / p, kh = y % p;
+  const long long row = (f * gh + ph) * gw + pw;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int px = 0; px < 8; ++px) {
+      const int byte = px * 3 + ch;
+      const float x = static_cast<float>((w[byte >> 2] >> ((byte & 3) * 8)) & 0xffu);
+      v[px] = __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.f), mean[ch]), sd[ch]);
+    }
+    *reinterpret_cast<uint4*>(out + row * (3 * p * p) + ch * p * p + kh * p + kw) = pack8f(v);
+  }
+}
+
 // ------------------------------------------------------------ embedding tables
 // table[t*L + l, :] = interp(temporal)[t, :] + pos[1 + l, :]      (bf16; the patch GEMM adds it as a periodic residual)
 // x[b, m, :]       = (m == 0 ? class_embedding : added_cls[m-1]) + pos[0, :]   for m < M
@@ -246,6 +284,20 @@ extern "C" int xp_vip_patchify(const void* video, int32_t dtype, void* patches_b
   else
     return fail("xp_vip_patchify: dtype must be XP_DTYPE_F32 / BF16 / F16");
   XP_CHECK_LAUNCH("patchify_kernel");
+  return 0;
+}
+
+extern "C" int xp_vip_patchify_u8(const uint8_t* frames_hwc, void* patches_bf16, int64_t frames, int32_t H, int32_t W,
+                                  int32_t patch, const float* mean3, const float* std3, void* stream) {
+  XP_ENTER(frames_hwc);
+  if (patch % 8 || W % patch || H % patch) return fail("xp_vip_patchify_u8: patch must be a multiple of 8 dividing H and W");
+  if ((reinterpret_cast<uintptr_t>(frames_hwc) & 7) != 0) return fail("xp_vip_patchify_u8: frames must be 8-byte aligned");
+  const long long total = frames * H * (W / 8);
+  if (total <= 0) return 0;
+  patchify_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames_hwc, static_cast<__nv_bfloat16*>(patches_bf16), frames, H, W, patch, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
+      std3[2]);
+  XP_CHECK_LAUNCH("patchify_u8_kernel");
   return 0;
 }
 

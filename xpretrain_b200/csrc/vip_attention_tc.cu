@@ -21,6 +21,7 @@
 #include "../../include/xpretrain_b200.h"
 #include "common.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace xp {
 
@@ -412,7 +413,10 @@ __device__ __forceinline__ uint32_t tb_col_mask(int i, int wg, int L, int M, boo
 
 __global__ void __launch_bounds__(TB_THREADS, 1)
 vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restrict__ lse, const float* __restrict__ delta,
-                       __nv_bfloat16* __restrict__ dqkv, float* __restrict__ gpart, const TcDims d, float q_scale) {
+                       __nv_bfloat16* __restrict__ dqkv, float* __restrict__ gpart, const TcDims d, float q_scale,
+                       const int dbg) {
+  // dbg (profiling only, XP_ATTN_BWD_DEBUG): bit 0 = issue no MMAs (commits only), bit 1 = math warps run the barrier
+  // protocol without their loads / exps / stores — isolates the tensor-pipe time from the math time
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -491,6 +495,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
                      sP = base + TB_SP, sdS = base + TB_SDS;
       // the three gradient products of step (i, j) with K' in buffer kb
       auto issue_grads = [&](int i, int j, int kb) {
+        if (dbg & 1) return;
         const uint32_t sK = base + TB_SK + kb * TB_KBUF, sKg = sK + TC_FK * 128;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {   // K = the 128 query rows of tile j
@@ -533,7 +538,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
           if (step > 0) mbar_wait(&bar[S_FREE], (step - 1) & 1);      // phase 1 of the previous step has read its S
           tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
+          for (int ks = 0; ks < ((dbg & 1) ? 0 : 4); ++ks) {
             const uint64_t aq = make_smem_desc_sw128(sQ + j * 16384 + ks * 32, 16, 1024);
             const uint32_t acc = ks > 0 ? 1u : 0u;
             if (i == 0) {
@@ -553,7 +558,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
           }
           tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
+          for (int ks = 0; ks < ((dbg & 1) ? 0 : 4); ++ks) {
             const uint64_t ao = make_smem_desc_sw128(sdO + j * 16384 + ks * 32, 16, 1024);
             const uint32_t acc = ks > 0 ? 1u : 0u;
             if (i == 0) {
@@ -693,7 +698,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         const int row = j * 128 + trow;
         const bool q_glob = row >= TC_GROW && row < TC_GROW + d.M;
         const bool cols_on = i == 0 ? (wg * 32 < d.L) : (wg < 3);
-        const bool active = warp_live[j] && cols_on;
+        const bool active = warp_live[j] && cols_on && !(dbg & 2);
         const uint32_t mask = tb_col_mask(i, wg, d.L, d.M, q_glob && t != 0);
         // ---- phase 1: P = exp(S - lse) -> packed bf16 in registers
         uint32_t ppk[16];
@@ -830,8 +835,9 @@ extern "C" int xp_vip_attention_bwd_tc_partial(const void* qkv, const void* out,
   if (make_tmap_bf16_2d(&tm.do_a, dout, C, rows, d.ld_o, TC_HD, L1)) return -1;
   if (make_tmap_bf16_2d(&tm.do_b, dout, C, rows, d.ld_o, TC_HD, L2 > 0 ? L2 : 1)) return -1;
   if (make_tmap_bf16_2d(&tm.do_g, dout, C, rows, d.ld_o, TC_HD, M)) return -1;
+  static const int dbg = [] { const char* e = getenv("XP_ATTN_BWD_DEBUG"); return e ? atoi(e) : 0; }();
   vip_attn_bwd_tc_kernel<<<grid, TB_THREADS, smem, st>>>(tm, lse, delta, static_cast<__nv_bfloat16*>(dqkv), workspace, d,
-                                                         q_scale);
+                                                         q_scale, dbg);
   XP_CHECK_LAUNCH("vip_attn_bwd_tc_kernel");
   return 0;
 }

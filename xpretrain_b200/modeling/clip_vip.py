@@ -243,10 +243,11 @@ def _refresh_weights(model: CLIPModel) -> None:
                        ("small:vproj", model.visual_projection.weight), ("small:tproj", model.text_projection.weight)):
             pk[key] = torch.empty(p.shape, dtype=bf16, device=dev)
         pk["mirror"] = WeightMirror()
-    items = pk["vision"].items(model.vision_model.encoder.layers) + pk["text"].items(model.text_model.encoder.layers)
-    items += [(model.vision_model.embeddings.patch_embedding.weight, pk["small:patch"]),
-              (model.visual_projection.weight, pk["small:vproj"]), (model.text_projection.weight, pk["small:tproj"])]
-    pk["mirror"].refresh(items)
+        items = pk["vision"].items(model.vision_model.encoder.layers) + pk["text"].items(model.text_model.encoder.layers)
+        items += [(model.vision_model.embeddings.patch_embedding.weight, pk["small:patch"]),
+                  (model.visual_projection.weight, pk["small:vproj"]), (model.text_projection.weight, pk["small:tproj"])]
+        pk["items"] = items           # (Parameter, destination view) pairs: Parameter objects are stable, their .data may move
+    pk["mirror"].refresh(pk["items"])
 
 
 def _pack(model: CLIPModel, which: str) -> _WeightPack:
@@ -373,6 +374,8 @@ def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
     vm = model.vision_model
     emb = vm.embeddings
     B, T = video.shape[0], video.shape[1]
+    if video.dtype == torch.uint8 and (video.dim() != 5 or video.shape[-1] != 3):
+        raise ValueError("uint8 video must be channels-last [B, T, H, W, 3] (decoder layout)")
     C_, L, M = cfg.vision.hidden_size, cfg.num_patches, 1 + cfg.add_cls_num
     H = cfg.vision.num_attention_heads
     S = M + T * L
@@ -383,7 +386,11 @@ def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
     Kp = 3 * cfg.patch_size * cfg.patch_size
 
     patches = torch.empty(B * T * L, Kp, dtype=bf16, device=dev)
-    ops.vip_patchify(video.contiguous(), patches, cfg.patch_size)
+    if video.dtype == torch.uint8:      # raw decoder frames: the reference's /255 + Normalize is fused into the patch extraction
+        ops.vip_patchify_u8(video.contiguous(), patches, cfg.patch_size, getattr(model, "pixel_mean", ops.CLIP_MEAN),
+                            getattr(model, "pixel_std", ops.CLIP_STD))
+    else:
+        ops.vip_patchify(video.contiguous(), patches, cfg.patch_size)
     table = torch.empty(T * L, C_, dtype=bf16, device=dev)
     x0 = torch.empty(rows, C_, dtype=bf16, device=dev)
     temporal = emb.temporal_embedding if cfg.if_use_temporal_embed else None
@@ -458,8 +465,11 @@ def _vision_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str,
     ops.layernorm_bwd(dpooled, plain, sv.x_last, cls_map, vm.post_layernorm.weight, sv.meanp, sv.rstdp, None, None, dx,
                       cls_map, grads["vision_model.post_layernorm.weight"], grads["vision_model.post_layernorm.bias"], B, C_)
 
+    delta = torch.empty(B, H, S, dtype=f32, device=dev)       # rowsum(dO * O), scratch of the attention backward
+
     def attn_bwd(qkv, a, da, lse, dqkv):
-        ops.vip_attention_bwd(qkv, a, da, lse, dqkv, sv.ws, B, H, T, L, M, C_, pk.q_scale)
+        # pipelined tcgen05 / TMEM backward (csrc/vip_attention_tc.cu); the mma.sync kernel of round 1 stays as a cross-check in tests
+        ops.vip_attention_bwd_tc(qkv, a, da, lse, dqkv, sv.ws, delta, B, H, T, L, M, C_, pk.q_scale)
 
     timer = getattr(model, "block_timer", None)
     for i in reversed(range(len(vm.encoder.layers))):

@@ -171,6 +171,18 @@ def vip_patchify(video: torch.Tensor, patches: torch.Tensor, patch: int):
                                 _stream()), "xp_vip_patchify")
 
 
+CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)   # dataloader.py:213-214
+
+
+def vip_patchify_u8(frames_hwc: torch.Tensor, patches: torch.Tensor, patch: int, mean=CLIP_MEAN, std=CLIP_STD):
+    """frames_hwc uint8 [..., H, W, 3] -> normalised bf16 patch matrix (the reference's /255 + Normalize fused in)."""
+    assert frames_hwc.dtype == torch.uint8 and frames_hwc.is_contiguous() and frames_hwc.shape[-1] == 3
+    H, W = frames_hwc.shape[-3], frames_hwc.shape[-2]
+    n = frames_hwc.numel() // (3 * H * W)
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    check(lib().xp_vip_patchify_u8(_p(frames_hwc), _p(patches), n, H, W, patch, m3, s3, _stream()), "xp_vip_patchify_u8")
+
+
 def vip_embed_tables(pos, temporal, cls, added, table, x, B, T, L, M, C_, temporal_size):
     check(lib().xp_vip_embed_tables(_p(pos), _p(temporal), _p(cls), _p(added), _p(table), _p(x), B, T, L, M, C_,
                                     temporal_size, _stream()), "xp_vip_embed_tables")
