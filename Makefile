@@ -29,7 +29,11 @@ $(LIB): $(OBJS)
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean
+# per-kernel SASS mnemonic counts (UTCHMMA / UTMALDG / LDTM / STTM / HMMA ...) -> profiles/r02_sass.md
+sass: $(LIB)
+	python tools/sass_census.py $(LIB) > profiles/r02_sass.md
+
+.PHONY: all clean sass
 
 # standalone GPU self-tests (no torch); run on the GPU box
 TOOLS := build/gemm_selftest

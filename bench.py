@@ -103,10 +103,17 @@ def run_ours(args):
     from xpretrain_b200.optimization.loss import gather_nce_loss
     from xpretrain_b200.utils import distributed as xdist
 
+    # N > 1: the overlapped gradient all-reduce needs ~9 GB/s of a 900 GB/s fabric — give NCCL a handful of CTAs and keep them
+    # off the SMs of the persistent GEMMs (XP_SM_RESERVE SMs are left out of every GEMM grid; 0 disables)
+    reserve = int(os.environ.get("XP_SM_RESERVE", "4")) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0
+    if reserve > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
     rank, local, world = xdist.init_from_env("nccl")
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
+    if reserve > 0:
+        ops.set_sm_limit(torch.cuda.get_device_properties(local).multi_processor_count - reserve)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, T, Lt = args.batch, T_FRAMES, L_TOK
@@ -303,6 +310,7 @@ def run_ours(args):
                                f"{'/[2]' if world > 1 else ''}); step = fwd + gather + InfoNCE + bwd"
                                f"{' + DP grad all-reduce' if world > 1 else ''}",
                    "global_batch": pairs, "frames": T, "tokens": Lt, "parallelism": f"dp{world}",
+                   "sm_reserve_for_nccl": reserve,
                    "l2": "inputs (462 MB video + 40 GB activations per step) far exceed the 126 MB L2",
                    "weights": "random init with the reference's init statistics, fp32 masters, bf16 compute copies"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 3),

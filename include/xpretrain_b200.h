@@ -89,10 +89,13 @@ typedef struct XpRowMap {
 int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMap* ymap, const float* gamma,
                      const float* beta, float* mean, float* rstd, int64_t rows, int32_t C, float eps, void* stream);
 /* LayerNorm backward; dx = LN'(dy) + dres (the residual-branch gradient, may be NULL);
- * dgamma/dbeta are ACCUMULATED (fp32 atomics) so they can point at .grad buffers. */
+ * dgamma/dbeta are ACCUMULATED (fp32 atomics) so they can point at .grad buffers.  dres_colsum (optional, needs dres):
+ * ACCUMULATES sum_rows dres — the bias gradient of the Linear that closes the other branch of that residual add
+ * (fc2.bias / out_proj.bias of CLIPEncoderLayer, CLIP_ViP.py:445-460), so no separate column-sum pass reads dres again. */
 int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const void* x, const XpRowMap* xmap, const float* gamma,
                      const float* mean, const float* rstd, const void* dres, const XpRowMap* drmap, void* dx,
-                     const XpRowMap* dxmap, float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream);
+                     const XpRowMap* dxmap, float* dgamma, float* dbeta, float* dres_colsum, int64_t rows, int32_t C,
+                     void* stream);
 /* x / x.norm(dim=-1, keepdim=True) (CLIP_ViP.py:1148-1149), fp32. */
 int xp_l2norm_fwd(const float* x, float* y, float* inv_norm, int32_t rows, int32_t C, void* stream);
 int xp_l2norm_bwd(const float* dy, const float* y, const float* inv_norm, void* dx_bf16, int32_t rows, int32_t C,

@@ -135,3 +135,77 @@ def test_init_weights_statistics_follow_the_reference():
                 assert float((ln.weight - 1).abs().max()) == 0.0 and float(ln.bias.abs().max()) == 0.0
     close(std(m.visual_projection.weight), 768 ** -0.5); close(std(m.text_projection.weight), 512 ** -0.5)
     assert abs(float(m.logit_scale) - 4.60) < 1e-6
+
+
+def test_training_restorer_shaped_checkpoint_round_trips(tmp_path):
+    """E2E_TrainingRestorer (CLIP-ViP/src/utils/load_save.py:260-327): `restore.pt` = {'global_step', 'model_state_dict',
+    'optim_state_dict'} with every fp32 tensor stored as CPU fp16 (`_to_cpu`, :177-192) and turned back into fp32 on load
+    (`_to_cuda`, :159-174).  Our module tree and our AdamW must accept that file unchanged: same keys, same optimizer-state
+    layout (`step`, `exp_avg`, `exp_avg_sq`; param_groups with lr / betas / eps / weight_decay / correct_bias)."""
+    import torch
+    from types import SimpleNamespace
+    from xpretrain_b200.modeling import VidCLIP
+    from xpretrain_b200.modeling.clip_vip import ClipVipConfig, TowerConfig
+    from xpretrain_b200.optimization.adamw import AdamW, build_e2e_optimizer_w_lr_mul
+
+    def to_cpu(state):     # restatement of load_save.py:177-192
+        if isinstance(state, torch.Tensor):
+            ret = state.cpu()
+            return ret.half() if "Float" in state.type() else ret
+        if isinstance(state, (list, tuple)):
+            return type(state)(to_cpu(t) for t in state)
+        if isinstance(state, dict):
+            return {n: to_cpu(t) for n, t in state.items()}
+        return state
+
+    def to_f32(state):     # load_save.py:159-174 without the .cuda()
+        if isinstance(state, torch.Tensor):
+            return state.float() if "Half" in state.type() else state
+        if isinstance(state, (list, tuple)):
+            return type(state)(to_f32(t) for t in state)
+        if isinstance(state, dict):
+            return {n: to_f32(t) for n, t in state.items()}
+        return state
+
+    def build(seed):
+        torch.manual_seed(seed)
+        add = SimpleNamespace(type="ViP", temporal_size=12, if_use_temporal_embed=1, logit_scale_init_value=4.6, add_cls_num=3)
+        mc = ClipVipConfig(vision=TowerConfig(768, 12, 1, 3072), text=TowerConfig(512, 8, 1, 2048))
+        model = VidCLIP(SimpleNamespace(clip_config=mc, clip_weights="", clip_vision_additional_config=add))
+        opt = AdamW(build_e2e_optimizer_w_lr_mul(list(model.named_parameters()), 1e-4, 0.2), lr=1e-4, betas=(0.9, 0.98))
+        return model, opt
+
+    model, opt = build(0)
+    g = torch.Generator().manual_seed(3)
+    for group in opt.param_groups:                       # optimizer state in the reference layout (adamw.py:64-70)
+        for p in group["params"]:
+            opt.state[p] = {"step": 17, "exp_avg": torch.randn(p.shape, generator=g) * 1e-3,
+                            "exp_avg_sq": torch.rand(p.shape, generator=g) * 1e-6}
+    ckpt = {"global_step": 17, "model_state_dict": to_cpu(model.state_dict()), "optim_state_dict": to_cpu(opt.state_dict())}
+    assert set(ckpt["optim_state_dict"]["param_groups"][0]) >= {"lr", "betas", "eps", "weight_decay", "correct_bias", "params"}
+    path = tmp_path / "restore.pt"
+    torch.save(ckpt, path)
+
+    model2, opt2 = build(1)                              # different init: everything must come from the file
+    loaded = torch.load(path, weights_only=False)
+    model2.load_state_dict(to_f32(loaded["model_state_dict"]))
+    opt2.load_state_dict(to_f32(loaded["optim_state_dict"]))
+    for (n, a), (_, b) in zip(model.state_dict().items(), model2.state_dict().items()):
+        want = a.half().float() if a.is_floating_point() else a
+        assert torch.equal(b, want), n                   # fp16 storage is the reference's choice; the round trip adds nothing
+        assert b.dtype == a.dtype
+    for g1, g2 in zip(opt.param_groups, opt2.param_groups):
+        assert {k: v for k, v in g1.items() if k != "params"} == {k: v for k, v in g2.items() if k != "params"}
+        for p1, p2 in zip(g1["params"], g2["params"]):
+            s1, s2 = opt.state[p1], opt2.state[p2]
+            assert s2["step"] == 17 and s2["exp_avg"].dtype == torch.float32
+            assert torch.equal(s2["exp_avg"], s1["exp_avg"].half().float())
+            assert torch.equal(s2["exp_avg_sq"], s1["exp_avg_sq"].half().float())
+    # load_state_dict_with_mismatch (load_save.py:86-115): shape-mismatched and unknown keys are skipped silently
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["clipmodel.vision_model.embeddings.temporal_embedding"] = torch.zeros(1, 8, 768)
+    sd["task_head.weight"] = torch.zeros(3)
+    own = model2.state_dict()
+    toload = {k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}
+    missing, unexpected = model2.load_state_dict(toload, strict=False)
+    assert unexpected == [] and missing == ["clipmodel.vision_model.embeddings.temporal_embedding"]

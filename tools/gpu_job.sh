@@ -9,4 +9,5 @@ TMO=600 run r02_ncu_attn_bwd ncu --set full --import-source on --clock-control n
 TMO=900 run r02_t_parity python -m pytest tests/test_gpu_parity.py -q -s
 TMO=600 run r02_t_boundary python -m pytest tests/test_gpu_boundary.py tests/test_gpu_optim.py tests/test_gpu_metrics.py -q -s
 TMO=300 run r02_smoke python -c "import __graft_entry__ as g; g.smoke()"
+XP_NO_OVERLAP=1 TMO=600 run r02_bench_nooverlap python bench.py --steps 5 --warmup 3 --no-eager
 TMO=900 run r02_bench python bench.py --steps 5 --warmup 3

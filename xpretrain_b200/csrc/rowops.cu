@@ -104,23 +104,30 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowMapDev xm, __nv_bfloat16* 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma;
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy  (fp32 atomics, one per column per CTA).
 constexpr int LNB_WARPS = 8;
-template <int NVEC>
+// RSUM: additionally accumulate the column sums of dres into dres_sum — dres is the gradient of a residual add whose other
+// branch ends in a Linear, so its column sum IS that Linear's bias gradient (fc2.bias from LN2's dres, out_proj.bias from
+// LN1's): the pass that already streams dres produces it, and the standalone colsum launches disappear.
+template <int NVEC, bool RSUM>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const __nv_bfloat16* __restrict__ x, RowMapDev xm,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const __nv_bfloat16* __restrict__ dres, RowMapDev drm, __nv_bfloat16* __restrict__ dx, RowMapDev dxm,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
-  extern __shared__ float red[];  // [LNB_WARPS][2][C], gamma staged behind it
-  float* sgamma = red + LNB_WARPS * 2 * C;
+              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dres_sum, long long rows, int C) {
+  constexpr int NACC = RSUM ? 3 : 2;
+  extern __shared__ float red[];  // [LNB_WARPS][NACC][C], gamma staged behind it
+  float* sgamma = red + LNB_WARPS * NACC * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = C >> 3;
   for (int c = threadIdx.x; c < C; c += blockDim.x) sgamma[c] = gamma[c];
   __syncthreads();
-  float ag[NVEC][8], ab[NVEC][8];
+  float ag[NVEC][8], ab[NVEC][8], ar[RSUM ? NVEC : 1][8];
 #pragma unroll
   for (int i = 0; i < NVEC; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      ag[i][j] = ab[i][j] = 0.f;
+      if (RSUM) ar[i][j] = 0.f;
+    }
   for (long long r = static_cast<long long>(blockIdx.x) * LNB_WARPS + warp; r < rows;
        r += static_cast<long long>(gridDim.x) * LNB_WARPS) {
     const __nv_bfloat16* xr = x + row_addr(xm, r);
@@ -175,7 +182,10 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const __nv_bf
           float rv[8];
           unpack8(rraw[i], rv);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+          for (int j = 0; j < 8; ++j) {
+            o[j] += rv[j];
+            if (RSUM) ar[i][j] += rv[j];
+          }
         }
         *reinterpret_cast<uint4*>(dxr + c * 8) = pack8(o);
       }
@@ -188,21 +198,24 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const __nv_bf
     if (c < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        red[(warp * 2 + 0) * C + c * 8 + j] = ag[i][j];
-        red[(warp * 2 + 1) * C + c * 8 + j] = ab[i][j];
+        red[(warp * NACC + 0) * C + c * 8 + j] = ag[i][j];
+        red[(warp * NACC + 1) * C + c * 8 + j] = ab[i][j];
+        if (RSUM) red[(warp * NACC + 2) * C + c * 8 + j] = ar[i][j];
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float sg = 0.f, sb = 0.f;
+    float sg = 0.f, sb = 0.f, sr = 0.f;
 #pragma unroll
     for (int w = 0; w < LNB_WARPS; ++w) {
-      sg += red[(w * 2 + 0) * C + c];
-      sb += red[(w * 2 + 1) * C + c];
+      sg += red[(w * NACC + 0) * C + c];
+      sb += red[(w * NACC + 1) * C + c];
+      if (RSUM) sr += red[(w * NACC + 2) * C + c];
     }
     atomicAdd(dgamma + c, sg);
     atomicAdd(dbeta + c, sb);
+    if (RSUM) atomicAdd(dres_sum + c, sr);
   }
 }
 
@@ -530,32 +543,40 @@ extern "C" int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, co
 extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const void* x, const XpRowMap* xmap,
                                 const float* gamma, const float* mean, const float* rstd, const void* dres,
                                 const XpRowMap* drmap, void* dx, const XpRowMap* dxmap, float* dgamma, float* dbeta,
-                                int64_t rows, int32_t C, void* stream) {
+                                float* dres_colsum, int64_t rows, int32_t C, void* stream) {
   XP_ENTER(dy);
   if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_bwd: C must be a multiple of 8 and <= 1024");
+  if (dres_colsum != nullptr && dres == nullptr) return fail("xp_layernorm_bwd: dres_colsum needs dres");
   if (rows <= 0) return 0;
   long long want = (rows + LNB_WARPS - 1) / LNB_WARPS;
   const int grid = static_cast<int>(want < 4LL * sm_count() ? want : 4LL * sm_count());
-  const size_t smem = (static_cast<size_t>(LNB_WARPS) * 2 + 1) * C * sizeof(float);
+  const bool rsum = dres_colsum != nullptr;
+  const size_t smem = (static_cast<size_t>(LNB_WARPS) * (rsum ? 3 : 2) + 1) * C * sizeof(float);
   XpRowMap none = {0, 0, 0, nullptr};
   const int nv = (C / 8 + 31) / 32;
-#define XP_LNB_LAUNCH(NV)                                                                                           \
+#define XP_LNB_LAUNCH(NV, RS)                                                                                       \
   do {                                                                                                              \
     static bool attr = false;                                                                                       \
     if (!attr) {                                                                                                    \
-      XP_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                         (LNB_WARPS * 2 + 1) * 1024 * 4));                                          \
+      XP_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                         (LNB_WARPS * (RS ? 3 : 2) + 1) * 1024 * 4));                               \
       attr = true;                                                                                                  \
     }                                                                                                               \
-    ln_bwd_kernel<NV><<<grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                           \
+    ln_bwd_kernel<NV, RS><<<grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                       \
         static_cast<const __nv_bfloat16*>(dy), to_dev(*dymap), static_cast<const __nv_bfloat16*>(x), to_dev(*xmap), \
         gamma, mean, rstd, static_cast<const __nv_bfloat16*>(dres), to_dev(drmap ? *drmap : none),                  \
-        static_cast<__nv_bfloat16*>(dx), to_dev(*dxmap), dgamma, dbeta, rows, C);                                   \
+        static_cast<__nv_bfloat16*>(dx), to_dev(*dxmap), dgamma, dbeta, dres_colsum, rows, C);                      \
   } while (0)
-  if (nv == 1) XP_LNB_LAUNCH(1);
-  else if (nv == 2) XP_LNB_LAUNCH(2);
-  else if (nv == 3) XP_LNB_LAUNCH(3);
-  else XP_LNB_LAUNCH(4);
+#define XP_LNB_PICK(NV)          \
+  do {                           \
+    if (rsum) XP_LNB_LAUNCH(NV, true);  \
+    else XP_LNB_LAUNCH(NV, false);      \
+  } while (0)
+  if (nv == 1) XP_LNB_PICK(1);
+  else if (nv == 2) XP_LNB_PICK(2);
+  else if (nv == 3) XP_LNB_PICK(3);
+  else XP_LNB_PICK(4);
+#undef XP_LNB_PICK
 #undef XP_LNB_LAUNCH
   XP_CHECK_LAUNCH("ln_bwd_kernel");
   return 0;

@@ -2,8 +2,8 @@
 // CLIP_ViP.py:332-381) — forward.  Persistent, warp-specialised, one CTA per SM looping over (batch, head, frame)
 // problems:
 //
-//   warps 0,2,3   producers: cp.async-stage the problem's q / k / v rows into shared memory in the UMMA
-//                 SWIZZLE_128B layout (double buffered, so problem n+1 loads while problem n computes)
+//   warp 0        TMA producer (one thread): six cp.async.bulk.tensor box loads stage the problem's q / k / v rows in shared
+//                 memory in the UMMA SWIZZLE_128B layout (double buffered: problem n+1 loads while problem n computes)
 //   warp 1        MMA issuer (one thread): S = Q' K'^T  (tcgen05.mma SS, fp32 in TMEM), then O = P V' with the A
 //                 operand read from TMEM (tcgen05.mma TS) and V' MN-major from shared memory
 //   warps 4-7     softmax warpgroup of query tile 0 (rows 0..127), one thread per TMEM lane
@@ -66,13 +66,14 @@ __device__ __forceinline__ float tc_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void tc_cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
 
 // part: [B, H, T, M, 66] fp32 = {max, sum, unnormalised out[64]} of the global queries over this frame's keys.
+struct TfMaps {
+  CUtensorMap qkv_f, qkv_g;     // boxes of 64 columns x {L frame rows, M global rows} over qkv [rows, 3C]
+};
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
+vip_attn_fwd_tc_kernel(const __grid_constant__ TfMaps tm, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                        float* __restrict__ part, const TcDims d) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -91,7 +92,7 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], 3);
+      mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
       mbar_init(&s_ready[i], 1);
       mbar_init(&p_ready[i], 128);
@@ -113,27 +114,31 @@ vip_attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 || warp == 2 || warp == 3) {
-    // ------------------------------------------- producers: warp 0 -> Q rows, warp 2 -> K rows, warp 3 -> V rows
-    const int mat = warp == 0 ? 0 : warp - 1;
-    const int chunk = lane & 7, r0 = lane >> 3;     // 4 rows x 8 sixteen-byte chunks per warp instruction
-    int n = 0;
-    for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
-      const int s = n & 1;
-      const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
-      mbar_wait(&empty[s], ((n >> 1) & 1) ^ 1);
-      const uint32_t sQ = buf0 + s * TC_BUF_BYTES, sK = sQ + TC_QROWS * 128, sV = sK + TC_FK * 128;
-      const uint32_t sKg = sV + TC_FK * 128, sVg = sKg + TC_GK * 128;
-      const uint32_t dstF = mat == 0 ? sQ : (mat == 1 ? sK : sV);
-      const uint32_t dstG = mat == 0 ? sQ + TC_GROW * 128 : (mat == 1 ? sKg : sVg);   // (TC_GROW & 7) == 0
-      const __nv_bfloat16* gsrc = qkv + static_cast<long long>(b) * d.S * d.ld_qkv + mat * d.C + h * TC_HD + chunk * 8;
-      const __nv_bfloat16* fsrc = gsrc + (d.M + static_cast<long long>(t) * d.L) * d.ld_qkv;
-      for (int row = r0; row < d.L; row += 4) tc_cp_async16(sw128(dstF, row, chunk), fsrc + static_cast<long long>(row) * d.ld_qkv);
-      for (int row = r0; row < d.M; row += 4) tc_cp_async16(sw128(dstG, row, chunk), gsrc + static_cast<long long>(row) * d.ld_qkv);
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
+  if (warp == 0) {
+    // ------------------------------------------- TMA producer (one thread): six box loads per problem — the L frame rows and
+    // the M global rows of the Q', K', V' head slices — land in the 128B-swizzled tiles the UMMA descriptors read
+    if (lane == 0) {
+      uint8_t* gbuf0 = smem_raw + (buf0 - raw);
+      int n = 0;
+      for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
+        const int s = n & 1;
+        const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
+        mbar_wait(&empty[s], ((n >> 1) & 1) ^ 1);
+        uint8_t* sQ = gbuf0 + s * TC_BUF_BYTES;
+        uint8_t* sK = sQ + TC_QROWS * 128;
+        uint8_t* sV = sK + TC_FK * 128;
+        uint8_t* sKg = sV + TC_FK * 128;
+        uint8_t* sVg = sKg + TC_GK * 128;
+        const int rg = static_cast<int>(static_cast<long long>(b) * d.S), rf = rg + d.M + t * d.L;
+        const int cq = h * TC_HD, ck = d.C + h * TC_HD, cv = 2 * d.C + h * TC_HD;
+        mbar_arrive_expect_tx(&full[s], 3u * static_cast<uint32_t>(d.L + d.M) * 128u);
+        tma_load_2d(sQ, &tm.qkv_f, &full[s], cq, rf);
+        tma_load_2d(sK, &tm.qkv_f, &full[s], ck, rf);
+        tma_load_2d(sQ + TC_GROW * 128, &tm.qkv_g, &full[s], cq, rg);      // (TC_GROW & 7) == 0: on a swizzle atom
+        tma_load_2d(sKg, &tm.qkv_g, &full[s], ck, rg);
+        tma_load_2d(sV, &tm.qkv_f, &full[s], cv, rf);
+        tma_load_2d(sVg, &tm.qkv_g, &full[s], cv, rg);
+      }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
@@ -322,8 +327,13 @@ extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float
   }
   const long long total = static_cast<long long>(B) * H * T;
   const int grid = static_cast<int>(total < sm_count() ? total : sm_count());
+  const long long rows = static_cast<long long>(B) * d.S;
+  if (rows >= (1LL << 31)) return fail("vip_attention: more than 2^31 token rows");
+  TfMaps tm;
+  if (make_tmap_bf16_2d(&tm.qkv_f, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, L)) return -1;
+  if (make_tmap_bf16_2d(&tm.qkv_g, qkv, 3ULL * C, rows, d.ld_qkv, TC_HD, M)) return -1;
   vip_attn_fwd_tc_kernel<<<grid, TC_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), lse, workspace, d);
+      tm, static_cast<__nv_bfloat16*>(out), lse, workspace, d);
   XP_CHECK_LAUNCH("vip_attn_fwd_tc_kernel");
   return 0;
 }

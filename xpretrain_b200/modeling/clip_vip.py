@@ -286,8 +286,20 @@ def _layer_fwd(x, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, rows: in
     return out, saved
 
 
+def _colsum(x: torch.Tensor, out: torch.Tensor, aux) -> None:
+    """Bias gradient = column sum of x (HBM-bound).  With an auxiliary stream it runs UNDER the tensor-bound GEMMs that follow
+    (its 256-thread CTAs co-reside with the persistent GEMM CTAs); the caller joins the stream before the gradients are used."""
+    if aux is None:
+        ops.colsum(x, out)
+        return
+    aux.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(aux):
+        ops.colsum(x, out)
+    x.record_stream(aux)
+
+
 def _layer_bwd(dx, saved, layer, pk: _WeightPack, i: int, grads: Dict[str, torch.Tensor], prefix: str, attn_bwd,
-               rows: int):
+               rows: int, aux=None):
     """Backward of one block; dx [rows, C] bf16 is d(loss)/d(block output).  Returns d(block input)."""
     (x, mean1, rstd1, h, qkv, att_saved, a, x1, mean2, rstd2, h2, pre, f1) = saved
     C_, I = pk.C, pk.I
@@ -296,34 +308,35 @@ def _layer_bwd(dx, saved, layer, pk: _WeightPack, i: int, grads: Dict[str, torch
     g = lambda n: grads[prefix + n]  # noqa: E731
     # ---- x_out = x1 + fc2(quick_gelu(fc1(LN2(x1))))
     ops.linear_wgrad(dx, f1, g("mlp.fc2.weight"))
-    ops.colsum(dx, g("mlp.fc2.bias"))
     dpre = torch.empty(rows, I, dtype=bf16, device=dev)
     ops.linear_dgrad(dx, pk.w2[i], dpre, act=_lib.ACT_DQUICK_GELU, aux=pre, ld_aux=I)
+    _colsum(dpre, g("mlp.fc1.bias"), aux)
     ops.linear_wgrad(dpre, h2, g("mlp.fc1.weight"))
-    ops.colsum(dpre, g("mlp.fc1.bias"))
     dh2 = torch.empty(rows, C_, dtype=bf16, device=dev)
     ops.linear_dgrad(dpre, pk.w1[i], dh2)
     del dpre
     dx1 = torch.empty(rows, C_, dtype=bf16, device=dev)
+    # LN2 backward streams dx as the residual-branch gradient: its column sum (= fc2.bias gradient) comes out of the same pass
     ops.layernorm_bwd(dh2, plain, x1, plain, layer.layer_norm2.weight, mean2, rstd2, dx, plain, dx1, plain,
-                      g("layer_norm2.weight"), g("layer_norm2.bias"), rows, C_)
+                      g("layer_norm2.weight"), g("layer_norm2.bias"), rows, C_, dres_colsum=g("mlp.fc2.bias"))
     # ---- x1 = x + out_proj(attn(qkv(LN1(x))))
     ops.linear_wgrad(dx1, a, g("self_attn.out_proj.weight"))
-    ops.colsum(dx1, g("self_attn.out_proj.bias"))
     da = dh2  # reuse
     ops.linear_dgrad(dx1, pk.wo[i], da)
     dqkv = torch.empty(rows, 3 * C_, dtype=bf16, device=dev)
     attn_bwd(qkv, a, da, att_saved, dqkv)
     dwqkv = grads[prefix + "self_attn.qkv.weight"]
     dbqkv = grads[prefix + "self_attn.qkv.bias"]
+    _colsum(dqkv, dbqkv, aux)
     ops.linear_wgrad(dqkv, h, dwqkv)
-    ops.colsum(dqkv, dbqkv)
     dh = da
     ops.linear_dgrad(dqkv, pk.wqkv[i], dh)
     del dqkv
     dxin = torch.empty(rows, C_, dtype=bf16, device=dev)
     ops.layernorm_bwd(dh, plain, x, plain, layer.layer_norm1.weight, mean1, rstd1, dx1, plain, dxin, plain,
-                      g("layer_norm1.weight"), g("layer_norm1.bias"), rows, C_)
+                      g("layer_norm1.weight"), g("layer_norm1.bias"), rows, C_, dres_colsum=g("self_attn.out_proj.bias"))
+    if aux is not None:
+        torch.cuda.current_stream().wait_stream(aux)      # this layer's bias gradients are complete
     return dxin
 
 
@@ -472,12 +485,13 @@ def _vision_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str,
         ops.vip_attention_bwd_tc(qkv, a, da, lse, dqkv, sv.ws, delta, B, H, T, L, M, C_, pk.q_scale)
 
     timer = getattr(model, "block_timer", None)
+    aux = _aux_stream(model, dev)
     for i in reversed(range(len(vm.encoder.layers))):
         prefix = f"vision_model.encoder.layers.{i}."
         if timer is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        dx = _layer_bwd(dx, sv.layers[i], vm.encoder.layers[i], pk, i, grads, prefix, attn_bwd, rows)
+        dx = _layer_bwd(dx, sv.layers[i], vm.encoder.layers[i], pk, i, grads, prefix, attn_bwd, rows, aux)
         if timer is not None:
             e1.record()
             timer.append(("bwd", e0, e1))
@@ -590,18 +604,14 @@ class _ClipVipFunction(torch.autograd.Function):
         ctx.model = model
         _refresh_weights(model)
         ctx.normalize = normalize
-        outs = []
         ctx.vis = ctx.txt = None
         dev = params[0].device
-        for which in ("vis", "txt"):
+
+        def run_tower(which):
             if which == "vis":
-                if video is None:
-                    outs.append(torch.empty(0, device=dev)); continue
                 tower_save = save and any(r for n, r in need.items() if n.startswith(("vision_model.", "visual_projection.")))
                 proj, sv = _vision_fwd(model, video, tower_save)
             else:
-                if input_ids is None:
-                    outs.append(torch.empty(0, device=dev)); continue
                 # a frozen text tower (VidCLIP.freeze_text_encoder) keeps nothing and runs no backward
                 tower_save = save and any(r for n, r in need.items() if n.startswith(("text_model.", "text_projection.")))
                 proj, sv = _text_fwd(model, input_ids, attention_mask, tower_save)
@@ -614,8 +624,25 @@ class _ClipVipFunction(torch.autograd.Function):
             if sv is not None:
                 sv.feat, sv.inv = feat, inv
                 setattr(ctx, which, sv)
-            outs.append(feat)
-        return tuple(outs)
+            return feat
+
+        none = torch.empty(0, device=dev)
+        side = _side_stream(model, dev) if (video is not None and input_ids is not None) else None
+        ctx.side = side
+        if side is None:
+            vis = run_tower("vis") if video is not None else none
+            txt = run_tower("txt") if input_ids is not None else none
+        else:
+            # The text tower (~300 launches of microsecond kernels) runs on a side stream under the vision
+            # tower: its small grids fill the SMs that the persistent vision kernels leave idle in their last wave.
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                txt = run_tower("txt")
+            vis = run_tower("vis")
+            main.wait_stream(side)
+            txt.record_stream(main)
+        return vis, txt
 
     @staticmethod
     def backward(ctx, d_vis, d_txt):
@@ -627,32 +654,72 @@ class _ClipVipFunction(torch.autograd.Function):
         C_v, C_t = model.config.vision.hidden_size, model.config.text.hidden_size
         jobs = (("vision_model", ctx.vis, d_vis, "visual_projection.weight", _vision_bwd, C_v),
                 ("text_model", ctx.txt, d_txt, "text_projection.weight", _text_bwd, C_t))
-        for tower, sv, dfeat, proj_name, bwd, C_ in jobs:
+        main = torch.cuda.current_stream()
+        side = ctx.side if (ctx.vis is not None and ctx.txt is not None and d_vis is not None and d_txt is not None) else None
+        for tower, sv, dfeat, proj_name, bwd, C_ in reversed(jobs) if side is not None else jobs:
             if sv is None or dfeat is None:
                 continue
-            tw = getattr(model, tower)
-            for i, layer in enumerate(tw.encoder.layers):
-                pre = f"{tower}.encoder.layers.{i}."
-                grads["__flat__" + pre] = _alloc_layer_grads(layer, pre, grads, dev)
-            rest = {n: tuple(named[n].shape) for n in names if n.startswith(tower + ".") and ".encoder.layers." not in n}
-            rest[proj_name] = tuple(named[proj_name].shape)
-            grads["__flat__" + tower] = _alloc_flat(rest, grads, dev)
-            dproj = torch.empty(dfeat.shape, dtype=bf16, device=dev)
-            dfeat = dfeat.contiguous().to(f32)
-            if ctx.normalize:
-                ops.l2norm_bwd(dfeat, sv.feat, sv.inv, dproj)
-            else:
-                dproj.copy_(dfeat)
-            bwd(model, dproj, sv, grads)
-            _grads_ready(model, grads, tower)
-            for i in range(len(tw.encoder.layers)):
-                _finish_layer_grads(f"{tower}.encoder.layers.{i}.", grads, C_)
+            on_side = side is not None and tower == "text_model"
+            if on_side:        # text backward first in issue order, on the side stream, under the vision backward
+                side.wait_stream(main)
+                dfeat.record_stream(side)
+                with torch.cuda.stream(side):
+                    _tower_backward(model, ctx, tower, sv, dfeat, proj_name, bwd, C_, grads, names, named, dev)
+                continue
+            _tower_backward(model, ctx, tower, sv, dfeat, proj_name, bwd, C_, grads, names, named, dev)
+        if side is not None:
+            main.wait_stream(side)
+            for k, t in grads.items():      # allocated in the side stream's pool, consumed by autograd on the main stream
+                if k.startswith("__flat__text_model"):
+                    t.record_stream(main)
         hook = getattr(model, "grad_ready_hook", None)
         if hook is not None and hasattr(hook, "finish"):
             hook.finish()      # stream-ordered wait: autograd's accumulation below sees the averaged values
         ctx.vis = ctx.txt = None
         return (None, None, None, None, None, None) + tuple(grads.get(n) if r else None
                                                              for n, r in zip(names, ctx.needs_input_grad[6:]))
+
+
+def _tower_backward(model, ctx, tower, sv, dfeat, proj_name, bwd, C_, grads, names, named, dev):
+    tw = getattr(model, tower)
+    for i, layer in enumerate(tw.encoder.layers):
+        pre = f"{tower}.encoder.layers.{i}."
+        grads["__flat__" + pre] = _alloc_layer_grads(layer, pre, grads, dev)
+    rest = {n: tuple(named[n].shape) for n in names if n.startswith(tower + ".") and ".encoder.layers." not in n}
+    rest[proj_name] = tuple(named[proj_name].shape)
+    grads["__flat__" + tower] = _alloc_flat(rest, grads, dev)
+    dproj = torch.empty(dfeat.shape, dtype=bf16, device=dev)
+    dfeat = dfeat.contiguous().to(f32)
+    if ctx.normalize:
+        ops.l2norm_bwd(dfeat, sv.feat, sv.inv, dproj)
+    else:
+        dproj.copy_(dfeat)
+    bwd(model, dproj, sv, grads)
+    _grads_ready(model, grads, tower)
+    for i in range(len(tw.encoder.layers)):
+        _finish_layer_grads(f"{tower}.encoder.layers.{i}.", grads, C_)
+
+
+def _side_stream(model: CLIPModel, dev):
+    """Side stream for the text tower (None when `model.overlap_text_tower` is False or XP_NO_OVERLAP=1)."""
+    import os
+    if not getattr(model, "overlap_text_tower", True) or os.environ.get("XP_NO_OVERLAP") == "1":
+        return None
+    st = model._packs.get("side_stream")
+    if st is None or st.device != dev:
+        st = model._packs["side_stream"] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _aux_stream(model: CLIPModel, dev):
+    """Stream for the HBM-bound bias column sums of the vision backward (None: XP_NO_OVERLAP=1 / model.overlap_colsum False)."""
+    import os
+    if not getattr(model, "overlap_colsum", True) or os.environ.get("XP_NO_OVERLAP") == "1":
+        return None
+    st = model._packs.get("aux_stream")
+    if st is None or st.device != dev:
+        st = model._packs["aux_stream"] = torch.cuda.Stream(device=dev)
+    return st
 
 
 def _run(model: CLIPModel, video, input_ids, attention_mask, normalize: bool = True):

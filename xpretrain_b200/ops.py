@@ -57,7 +57,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.a_layout, g.b_layout, g.act, g.out = a_layout, b_layout, act, out_mode
     g.splits, g.scale_cols, g.alpha, g.col_scale = splits, scale_cols, alpha, col_scale
     g.c_group, g.c_group_stride, g.r_group, g.r_group_stride = c_group, c_group_stride, r_group, r_group_stride
-    g.block_n, g.max_ctas, g.cta_pair = block_n, 0, cta_pair
+    g.block_n, g.max_ctas, g.cta_pair = block_n, _sm_limit, cta_pair
     if _gemm_timer is None:
         check(lib().xp_gemm(C.byref(g), _stream()), "xp_gemm")
     else:  # bench.py's roofline leg: CUDA events on the launching stream around this launch
@@ -69,6 +69,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
 
 
 _gemm_timer = None
+_sm_limit = 0
+
+
+def set_sm_limit(n: int) -> None:
+    """Cap the persistent GEMM grids at n CTAs (0 = all SMs).  A data-parallel job reserves a few SMs this way for the NCCL
+    kernels of the overlapped gradient all-reduce (NCCL_MAX_CTAS), so that they never displace a persistent GEMM CTA — whose
+    tiles would then run as a second, nearly empty wave (`gemm_ms_per_step` 71.3 -> 74.7 ms from 1 to 8 GPUs)."""
+    global _sm_limit
+    _sm_limit = max(0, int(n)) // 2 * 2       # CTA pairs: keep it even
 
 
 def set_gemm_timer(records) -> None:
@@ -91,9 +100,10 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, **kw) -> N
     gemm(dy, w, dx, M=M, N=K, K=N, lda=dy.stride(0), ldb=w.stride(0), ldc=dx.stride(0), b_layout=1, **kw)
 
 
-def wgrad_plan(n_out: int, n_in: int, rows: int, sms: int = 148):
+def wgrad_plan(n_out: int, n_in: int, rows: int, sms: int = 0):
     """(block_n, splits) for a weight-gradient GEMM: the split-K factor that fills whole waves of the persistent grid.
     Outputs of at least 256 x 256 run on CTA pairs (256 x 256 tiles, sms/2 clusters), smaller ones on single CTAs."""
+    sms = sms or _sm_limit or 148
     pair = n_out >= 256 and n_in >= 256
     bn = 256 if n_in >= 256 else 128
     if pair:
@@ -134,11 +144,11 @@ def layernorm_fwd(x, xmap, y, ymap, gamma, beta, mean, rstd, rows: int, C_: int,
 
 
 def layernorm_bwd(dy, dymap, x, xmap, gamma, mean, rstd, dres, drmap, dx, dxmap, dgamma, dbeta, rows: int, C_: int,
-                  dy_off=0, x_off=0, dres_off=0, dx_off=0):
+                  dy_off=0, x_off=0, dres_off=0, dx_off=0, dres_colsum=None):
     check(lib().xp_layernorm_bwd(_p(dy) + dy_off * 2, C.byref(dymap), _p(x) + x_off * 2, C.byref(xmap), _p(gamma),
                                  _p(mean), _p(rstd), (_p(dres) + dres_off * 2) if dres is not None else None,
                                  C.byref(drmap) if drmap is not None else None, _p(dx) + dx_off * 2, C.byref(dxmap),
-                                 _p(dgamma), _p(dbeta), rows, C_, _stream()), "xp_layernorm_bwd")
+                                 _p(dgamma), _p(dbeta), _p(dres_colsum), rows, C_, _stream()), "xp_layernorm_bwd")
 
 
 def l2norm_fwd(x, y, inv_norm):
