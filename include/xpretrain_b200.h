@@ -88,12 +88,21 @@ typedef struct XpRowMap {
 /* nn.LayerNorm forward (CLIP_ViP.py:447,458,881,892,771): bf16 in/out, fp32 gamma/beta/statistics. */
 int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMap* ymap, const float* gamma,
                      const float* beta, float* mean, float* rstd, int64_t rows, int32_t C, float eps, void* stream);
+/* LayerNorm fused with the residual add of the block it opens (CLIPEncoderLayer, CLIP_ViP.py:445-460: `hidden = residual +
+ * branch; hidden = layer_normN(hidden)`), with the residual stream kept in fp32 as under the reference's autocast:
+ *   s = x (+ add_bf16);  sum_out = s (fp32, optional);  y = LayerNorm(s).
+ * x is bf16 or fp32 (x_dtype), y bf16 or fp32 (y_dtype); add / sum_out / their maps may be NULL (plain LayerNorm). */
+int xp_layernorm_add_fwd(const void* x, const XpRowMap* xmap, int32_t x_dtype, const void* add_bf16, const XpRowMap* addmap,
+                         float* sum_out, const XpRowMap* summap, void* y, const XpRowMap* ymap, int32_t y_dtype,
+                         const float* gamma, const float* beta, float* mean, float* rstd, int64_t rows, int32_t C, float eps,
+                         void* stream);
 /* LayerNorm backward; dx = LN'(dy) + dres (the residual-branch gradient, may be NULL);
  * dgamma/dbeta are ACCUMULATED (fp32 atomics) so they can point at .grad buffers.  dres_colsum (optional, needs dres):
  * ACCUMULATES sum_rows dres — the bias gradient of the Linear that closes the other branch of that residual add
- * (fc2.bias / out_proj.bias of CLIPEncoderLayer, CLIP_ViP.py:445-460), so no separate column-sum pass reads dres again. */
-int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const void* x, const XpRowMap* xmap, const float* gamma,
-                     const float* mean, const float* rstd, const void* dres, const XpRowMap* drmap, void* dx,
+ * (fc2.bias / out_proj.bias of CLIPEncoderLayer, CLIP_ViP.py:445-460), so no separate column-sum pass reads dres again.
+ * x (the saved LayerNorm input) is bf16 or fp32 (x_dtype); dy, dres, dx are bf16. */
+int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const void* x, const XpRowMap* xmap, int32_t x_dtype,
+                     const float* gamma, const float* mean, const float* rstd, const void* dres, const XpRowMap* drmap, void* dx,
                      const XpRowMap* dxmap, float* dgamma, float* dbeta, float* dres_colsum, int64_t rows, int32_t C,
                      void* stream);
 /* x / x.norm(dim=-1, keepdim=True) (CLIP_ViP.py:1148-1149), fp32. */

@@ -197,6 +197,42 @@ def test_uint8_frames_preprocessing_bit_exact_vs_reference_transform(dev):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("C", [768, 512])
+@pytest.mark.parametrize("x_f32", [True, False])
+def test_layernorm_with_fp32_residual_add_and_bias_colsum(dev, C, x_f32):
+    """`hidden = residual + branch; hidden = layer_norm(hidden)` (CLIP_ViP.py:445-460) in one kernel with the sum kept in fp32,
+    and its backward with an fp32 saved input + the residual-branch column sum (the closing Linear's bias gradient)."""
+    from xpretrain_b200 import ops
+    rows, eps = 517, 1e-5
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(rows, C, generator=g) * 2).to(dev)
+    x = x if x_f32 else x.to(bf16)
+    add = torch.randn(rows, C, generator=g).to(dev).to(bf16)
+    gamma, beta = (1 + 0.1 * torch.randn(C, generator=g)).to(dev), (0.1 * torch.randn(C, generator=g)).to(dev)
+    y = torch.empty(rows, C, dtype=bf16, device=dev)
+    s_out = torch.empty(rows, C, device=dev)
+    mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    m = ops.rowmap(C)
+    ops.layernorm_fwd(x, m, y, m, gamma, beta, mean, rstd, rows, C, eps, add=add, addmap=m, sum_out=s_out, summap=m)
+    want_s = x.float() + add.float()
+    assert torch.equal(s_out, want_s)                                               # one fp32 add: exact
+    sr = want_s.clone().requires_grad_(True)
+    want_y = F.layer_norm(sr, (C,), gamma, beta, eps)
+    assert rel(y, want_y.detach()) < 4e-3
+    y32 = torch.empty(rows, C, device=dev)                                          # fp32 output (pre_layrnorm -> stream)
+    ops.layernorm_fwd(x, m, y32, m, gamma, beta, None, None, rows, C, eps)
+    assert rel(y32, F.layer_norm(x.float(), (C,), gamma, beta, eps)) < 1e-5
+    dy = torch.randn(rows, C, generator=g).to(dev).to(bf16)
+    dres = torch.randn(rows, C, generator=g).to(dev).to(bf16)
+    want_y.backward(dy.float())
+    dx = torch.empty(rows, C, dtype=bf16, device=dev)
+    dg, db, dsum = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    ops.layernorm_bwd(dy, m, s_out, m, gamma, mean, rstd, dres, m, dx, m, dg, db, rows, C, dres_colsum=dsum)
+    assert rel(dx, sr.grad + dres.float()) < 4e-3
+    assert rel(dsum, dres.float().sum(0)) < 1e-5
+    assert rel(db, dy.float().sum(0)) < 1e-5 and rel(dg, (dy.float() * ((want_s - want_s.mean(-1, keepdim=True)) * rstd[:, None])).sum(0)) < 1e-4
+
+
 def test_patchify_and_embed_tables(dev):
     from oracle import clipvip_oracle as O
     from xpretrain_b200 import ops

@@ -210,7 +210,9 @@ def test_hidden_states_against_oracle(dev):
     for i, want in enumerate(vh[:-1]):
         got = sv.layers[i][0].view(2, S, 768).cpu()          # saved input of layer i == hidden state i
         assert _rel(got, want) < 8e-3, i
-    assert _rel(sv.x_last.view(2, S, 768).cpu(), vh[-1]) < 1e-2
+    xl, pend = sv.x_last                                          # fp32 residual stream + the last block's bf16 branch output
+    last = xl.float() + (pend.float() if pend is not None else 0)
+    assert _rel(last.view(2, S, 768).cpu(), vh[-1]) < 1e-2
 
 
 def test_full_size_properties(dev):

@@ -59,7 +59,10 @@ SIGNATURES = {
     "xp_gemm": (c_int, [P(XpGemm), c_void_p]),
     "xp_layernorm_fwd": (c_int, [c_void_p, P(XpRowMap), c_void_p, P(XpRowMap), c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_i64, c_int, c_float, c_void_p]),
-    "xp_layernorm_bwd": (c_int, [c_void_p, P(XpRowMap), c_void_p, P(XpRowMap), c_void_p, c_void_p, c_void_p, c_void_p,
+    "xp_layernorm_add_fwd": (c_int, [c_void_p, P(XpRowMap), c_int, c_void_p, P(XpRowMap), c_void_p, P(XpRowMap), c_void_p,
+                                     P(XpRowMap), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float,
+                                     c_void_p]),
+    "xp_layernorm_bwd": (c_int, [c_void_p, P(XpRowMap), c_void_p, P(XpRowMap), c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  P(XpRowMap), c_void_p, P(XpRowMap), c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "xp_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "xp_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),

@@ -46,22 +46,57 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ------------------------------------------------------------------ LayerNorm forward
+// Optionally fused with the residual add in fp32 (the reference keeps the residual stream in fp32 under autocast; a bf16
+// stream costs ~2.4x its feature error, profiles/r02_parity_calibration.md):  s = x (+ add);  sum_out = s (fp32);
+// y = LN(s).  x is bf16 or fp32 (XF32), y bf16 or fp32 (YF32), add is the bf16 branch output (ADD).
+template <bool F32>
+__device__ __forceinline__ void ld8(const void* base, long long off, float (&f)[8]) {
+  if (F32) {
+    const float* p = static_cast<const float*>(base) + off;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8(*reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + off), f);
+  }
+}
+template <bool F32>
+__device__ __forceinline__ void st8(void* base, long long off, const float (&f)[8]) {
+  if (F32) {
+    float* p = static_cast<float*>(base) + off;
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(base) + off) = pack8(f);
+  }
+}
+
+template <bool XF32, bool YF32, bool ADD>
 __global__ void __launch_bounds__(128)
-ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowMapDev xm, __nv_bfloat16* __restrict__ y, RowMapDev ym,
+ln_fwd_kernel(const void* __restrict__ x, RowMapDev xm, const __nv_bfloat16* __restrict__ add, RowMapDev am,
+              float* __restrict__ sum_out, RowMapDev sm, void* __restrict__ y, RowMapDev ym,
               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, long long rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int nvec = C >> 3;
-  const __nv_bfloat16* xr = x + row_addr(xm, r);
+  const long long xo = row_addr(xm, r);
+  const long long ao = ADD ? row_addr(am, r) : 0;
+  const long long so = (ADD && sum_out) ? row_addr(sm, r) : 0;
   float v[LN_MAX_VEC][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < LN_MAX_VEC; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
-      unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), v[i]);
+      ld8<XF32>(x, xo + c * 8, v[i]);
+      if (ADD) {
+        float a[8];
+        unpack8(*reinterpret_cast<const uint4*>(add + ao + c * 8), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += a[j];
+        if (sum_out) st8<true>(sum_out, so + c * 8, v[i]);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     }
@@ -79,7 +114,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowMapDev xm, __nv_bfloat16* 
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / C + eps);
-  __nv_bfloat16* yr = y + row_addr(ym, r);
+  const long long yo = row_addr(ym, r);
 #pragma unroll
   for (int i = 0; i < LN_MAX_VEC; ++i) {
     const int c = lane + i * 32;
@@ -91,7 +126,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowMapDev xm, __nv_bfloat16* 
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
-      *reinterpret_cast<uint4*>(yr + c * 8) = pack8(o);
+      st8<YF32>(y, yo + c * 8, o);
     }
   }
   if (lane == 0) {
@@ -107,9 +142,9 @@ constexpr int LNB_WARPS = 8;
 // RSUM: additionally accumulate the column sums of dres into dres_sum — dres is the gradient of a residual add whose other
 // branch ends in a Linear, so its column sum IS that Linear's bias gradient (fc2.bias from LN2's dres, out_proj.bias from
 // LN1's): the pass that already streams dres produces it, and the standalone colsum launches disappear.
-template <int NVEC, bool RSUM>
+template <int NVEC, bool RSUM, bool XF32>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 2)
-ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const __nv_bfloat16* __restrict__ x, RowMapDev xm,
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const void* __restrict__ x, RowMapDev xm,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               const __nv_bfloat16* __restrict__ dres, RowMapDev drm, __nv_bfloat16* __restrict__ dx, RowMapDev dxm,
               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dres_sum, long long rows, int C) {
@@ -130,16 +165,16 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const __nv_bf
     }
   for (long long r = static_cast<long long>(blockIdx.x) * LNB_WARPS + warp; r < rows;
        r += static_cast<long long>(gridDim.x) * LNB_WARPS) {
-    const __nv_bfloat16* xr = x + row_addr(xm, r);
+    const long long xo = row_addr(xm, r);
     const __nv_bfloat16* dyr = dy + row_addr(dym, r);
     const __nv_bfloat16* drr = dres ? dres + row_addr(drm, r) : nullptr;
     const float mu = mean[r], rs = rstd[r];
-    uint4 xraw[NVEC], draw[NVEC], rraw[NVEC];
+    uint4 xraw[XF32 ? 1 : NVEC], draw[NVEC], rraw[NVEC];     // an fp32 x is re-read (L1) in the second pass, not kept
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        xraw[i] = *reinterpret_cast<const uint4*>(xr + c * 8);
+        if (!XF32) xraw[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x) + xo + c * 8);
         draw[i] = *reinterpret_cast<const uint4*>(dyr + c * 8);
         if (drr) rraw[i] = *reinterpret_cast<const uint4*>(drr + c * 8);
       }
@@ -150,7 +185,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const __nv_bf
       const int c = lane + i * 32;
       if (c < nvec) {
         float xv[8], dv[8];
-        unpack8(xraw[i], xv);
+        if (XF32) ld8<true>(x, xo + c * 8, xv);
+        else unpack8(xraw[i], xv);
         unpack8(draw[i], dv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -171,7 +207,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const __nv_bf
       const int c = lane + i * 32;
       if (c < nvec) {
         float xv[8], dv[8], o[8];
-        unpack8(xraw[i], xv);
+        if (XF32) ld8<true>(x, xo + c * 8, xv);
+        else unpack8(xraw[i], xv);
         unpack8(draw[i], dv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -527,24 +564,50 @@ extern "C" int xp_rowscale_bf16(const void* x, const float* scale, const void* r
   return 0;
 }
 
-extern "C" int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMap* ymap,
-                                const float* gamma, const float* beta, float* mean, float* rstd, int64_t rows,
-                                int32_t C, float eps, void* stream) {
+extern "C" int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMap* ymap, const float* gamma,
+                                const float* beta, float* mean, float* rstd, int64_t rows, int32_t C, float eps, void* stream) {
+  return xp_layernorm_add_fwd(x, xmap, XP_DTYPE_BF16, nullptr, nullptr, nullptr, nullptr, y, ymap, XP_DTYPE_BF16, gamma, beta,
+                              mean, rstd, rows, C, eps, stream);
+}
+
+extern "C" int xp_layernorm_add_fwd(const void* x, const XpRowMap* xmap, int32_t x_dtype, const void* add_bf16,
+                                    const XpRowMap* addmap, float* sum_out, const XpRowMap* summap, void* y,
+                                    const XpRowMap* ymap, int32_t y_dtype, const float* gamma, const float* beta, float* mean,
+                                    float* rstd, int64_t rows, int32_t C, float eps, void* stream) {
   XP_ENTER(x);
   if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_fwd: C must be a multiple of 8 and <= 1024");
+  if ((x_dtype != XP_DTYPE_BF16 && x_dtype != XP_DTYPE_F32) || (y_dtype != XP_DTYPE_BF16 && y_dtype != XP_DTYPE_F32))
+    return fail("xp_layernorm_add_fwd: x / y dtype must be XP_DTYPE_BF16 or XP_DTYPE_F32");
+  if (add_bf16 != nullptr && addmap == nullptr) return fail("xp_layernorm_add_fwd: add needs its row map");
+  if (sum_out != nullptr && (add_bf16 == nullptr || summap == nullptr)) return fail("xp_layernorm_add_fwd: sum_out needs add and its row map");
   if (rows <= 0) return 0;
-  ln_fwd_kernel<<<static_cast<unsigned>((rows + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), to_dev(*xmap), static_cast<__nv_bfloat16*>(y), to_dev(*ymap), gamma, beta,
-      mean, rstd, rows, C, eps);
+  const unsigned grid = static_cast<unsigned>((rows + 3) / 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XpRowMap none = {0, 0, 0, nullptr};
+  const RowMapDev xm = to_dev(*xmap), am = to_dev(addmap ? *addmap : none), sm = to_dev(summap ? *summap : none), ym = to_dev(*ymap);
+  const __nv_bfloat16* add = static_cast<const __nv_bfloat16*>(add_bf16);
+#define XP_LNF(XF, YF, AD) \
+  ln_fwd_kernel<XF, YF, AD><<<grid, 128, 0, st>>>(x, xm, add, am, sum_out, sm, y, ym, gamma, beta, mean, rstd, rows, C, eps)
+  const bool xf = x_dtype == XP_DTYPE_F32, yf = y_dtype == XP_DTYPE_F32, ad = add_bf16 != nullptr;
+  if (!xf && !yf && !ad) XP_LNF(false, false, false);
+  else if (!xf && !yf && ad) XP_LNF(false, false, true);
+  else if (!xf && yf && !ad) XP_LNF(false, true, false);
+  else if (!xf && yf && ad) XP_LNF(false, true, true);
+  else if (xf && !yf && !ad) XP_LNF(true, false, false);
+  else if (xf && !yf && ad) XP_LNF(true, false, true);
+  else if (xf && yf && !ad) XP_LNF(true, true, false);
+  else XP_LNF(true, true, true);
+#undef XP_LNF
   XP_CHECK_LAUNCH("ln_fwd_kernel");
   return 0;
 }
 
-extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const void* x, const XpRowMap* xmap,
+extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const void* x, const XpRowMap* xmap, int32_t x_dtype,
                                 const float* gamma, const float* mean, const float* rstd, const void* dres,
                                 const XpRowMap* drmap, void* dx, const XpRowMap* dxmap, float* dgamma, float* dbeta,
                                 float* dres_colsum, int64_t rows, int32_t C, void* stream) {
   XP_ENTER(dy);
+  if (x_dtype != XP_DTYPE_BF16 && x_dtype != XP_DTYPE_F32) return fail("xp_layernorm_bwd: x dtype must be XP_DTYPE_BF16 or XP_DTYPE_F32");
   if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_bwd: C must be a multiple of 8 and <= 1024");
   if (dres_colsum != nullptr && dres == nullptr) return fail("xp_layernorm_bwd: dres_colsum needs dres");
   if (rows <= 0) return 0;
@@ -554,23 +617,26 @@ extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const voi
   const size_t smem = (static_cast<size_t>(LNB_WARPS) * (rsum ? 3 : 2) + 1) * C * sizeof(float);
   XpRowMap none = {0, 0, 0, nullptr};
   const int nv = (C / 8 + 31) / 32;
-#define XP_LNB_LAUNCH(NV, RS)                                                                                       \
+  const bool xf32 = x_dtype == XP_DTYPE_F32;
+#define XP_LNB_LAUNCH(NV, RS, XF)                                                                                   \
   do {                                                                                                              \
     static bool attr = false;                                                                                       \
     if (!attr) {                                                                                                    \
-      XP_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+      XP_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV, RS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                          (LNB_WARPS * (RS ? 3 : 2) + 1) * 1024 * 4));                               \
       attr = true;                                                                                                  \
     }                                                                                                               \
-    ln_bwd_kernel<NV, RS><<<grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                       \
-        static_cast<const __nv_bfloat16*>(dy), to_dev(*dymap), static_cast<const __nv_bfloat16*>(x), to_dev(*xmap), \
+    ln_bwd_kernel<NV, RS, XF><<<grid, LNB_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                   \
+        static_cast<const __nv_bfloat16*>(dy), to_dev(*dymap), x, to_dev(*xmap),                                    \
         gamma, mean, rstd, static_cast<const __nv_bfloat16*>(dres), to_dev(drmap ? *drmap : none),                  \
         static_cast<__nv_bfloat16*>(dx), to_dev(*dxmap), dgamma, dbeta, dres_colsum, rows, C);                      \
   } while (0)
-#define XP_LNB_PICK(NV)          \
-  do {                           \
-    if (rsum) XP_LNB_LAUNCH(NV, true);  \
-    else XP_LNB_LAUNCH(NV, false);      \
+#define XP_LNB_PICK(NV)                                \
+  do {                                                 \
+    if (rsum && xf32) XP_LNB_LAUNCH(NV, true, true);   \
+    else if (rsum) XP_LNB_LAUNCH(NV, true, false);     \
+    else if (xf32) XP_LNB_LAUNCH(NV, false, true);     \
+    else XP_LNB_LAUNCH(NV, false, false);              \
   } while (0)
   if (nv == 1) XP_LNB_PICK(1);
   else if (nv == 2) XP_LNB_PICK(2);

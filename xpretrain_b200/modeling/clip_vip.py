@@ -49,6 +49,7 @@ class ClipVipConfig:
     vocab_size: int = 49408
     max_position_embeddings: int = 77
     layer_norm_eps: float = 1e-5
+    residual_fp32: bool = True          # keep the residual stream in fp32 (as the reference does under bf16 autocast)
     temporal_size: int = 12
     if_use_temporal_embed: int = 1
     add_cls_num: int = 3
@@ -259,31 +260,74 @@ def _small_bf16(model: CLIPModel, name: str, p: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- encoder layers
-def _layer_fwd(x, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, rows: int, save: bool):
-    """One pre-LN residual block (CLIP_ViP.py:445-460).  x: [rows, C] bf16.  Returns (x_out, saved)."""
+def _residual_fp32(model) -> bool:
+    """The residual stream is kept in fp32 (as under the reference's bf16 autocast, where only the Linear / matmul inputs are
+    rounded): the block outputs stay bf16 branch tensors and the add happens in fp32 inside the next LayerNorm kernel.
+    `model.config.residual_fp32 = False` (or XP_RESIDUAL_BF16=1) selects the round-1 path: bf16 stream, add in the GEMM epilogue."""
+    import os
+    return bool(getattr(model.config, "residual_fp32", True)) and os.environ.get("XP_RESIDUAL_BF16") != "1"
+
+
+def _layer_fwd(x, pend, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, rows: int, save: bool, fp32res: bool):
+    """One pre-LN residual block (CLIP_ViP.py:445-460).  x: residual stream [rows, C] (bf16, or fp32 with `fp32res`); pend: the
+    previous block's bf16 branch output that still has to be added to it (fp32res only).  Returns (x_out, pend_out, saved)."""
     C_, I = pk.C, pk.I
     dev = x.device
     plain = ops.rowmap(C_)
     mean1 = torch.empty(rows, dtype=f32, device=dev); rstd1 = torch.empty_like(mean1)
     h = torch.empty(rows, C_, dtype=bf16, device=dev)
-    ops.layernorm_fwd(x, plain, h, plain, layer.layer_norm1.weight, layer.layer_norm1.bias, mean1, rstd1, rows, C_, eps)
+    ln1, ln2 = layer.layer_norm1, layer.layer_norm2
+    if pend is not None:        # x <- x + pend in fp32, fused into layer_norm1
+        xs = torch.empty(rows, C_, dtype=f32, device=dev)
+        ops.layernorm_fwd(x, plain, h, plain, ln1.weight, ln1.bias, mean1, rstd1, rows, C_, eps, add=pend, addmap=plain,
+                          sum_out=xs, summap=plain)
+        x = xs
+    else:
+        ops.layernorm_fwd(x, plain, h, plain, ln1.weight, ln1.bias, mean1, rstd1, rows, C_, eps)
     qkv = torch.empty(rows, 3 * C_, dtype=bf16, device=dev)
     # q = (h Wq^T + bq) * head_dim**-0.5 : the scale multiplies the bias too (CLIP_ViP.py:341 / :269)
     ops.linear_fwd(h, pk.wqkv[i], pk.bqkv[i], qkv, scale_cols=C_, col_scale=pk.q_scale)
     a = torch.empty(rows, C_, dtype=bf16, device=dev)
     att_saved = attn_fwd(qkv, a)
-    x1 = torch.empty(rows, C_, dtype=bf16, device=dev)
-    ops.linear_fwd(a, pk.wo[i], layer.self_attn.out_proj.bias, x1, residual=x, ldr=C_)
     mean2 = torch.empty(rows, dtype=f32, device=dev); rstd2 = torch.empty_like(mean2)
     h2 = torch.empty(rows, C_, dtype=bf16, device=dev)
-    ops.layernorm_fwd(x1, plain, h2, plain, layer.layer_norm2.weight, layer.layer_norm2.bias, mean2, rstd2, rows, C_, eps)
+    if fp32res:
+        y1 = torch.empty(rows, C_, dtype=bf16, device=dev)
+        ops.linear_fwd(a, pk.wo[i], layer.self_attn.out_proj.bias, y1)                  # branch only: the add is in layer_norm2
+        x1 = torch.empty(rows, C_, dtype=f32, device=dev)
+        ops.layernorm_fwd(x, plain, h2, plain, ln2.weight, ln2.bias, mean2, rstd2, rows, C_, eps, add=y1, addmap=plain,
+                          sum_out=x1, summap=plain)
+        del y1
+    else:
+        x1 = torch.empty(rows, C_, dtype=bf16, device=dev)
+        ops.linear_fwd(a, pk.wo[i], layer.self_attn.out_proj.bias, x1, residual=x, ldr=C_)
+        ops.layernorm_fwd(x1, plain, h2, plain, ln2.weight, ln2.bias, mean2, rstd2, rows, C_, eps)
     pre = torch.empty(rows, I, dtype=bf16, device=dev) if save else None
     f1 = torch.empty(rows, I, dtype=bf16, device=dev)
     ops.linear_fwd(h2, pk.w1[i], layer.mlp.fc1.bias, f1, act=_lib.ACT_QUICK_GELU, aux=pre, ld_aux=I)
     out = torch.empty(rows, C_, dtype=bf16, device=dev)
-    ops.linear_fwd(f1, pk.w2[i], layer.mlp.fc2.bias, out, residual=x1, ldr=C_)
     saved = (x, mean1, rstd1, h, qkv, att_saved, a, x1, mean2, rstd2, h2, pre, f1) if save else None
-    return out, saved
+    if fp32res:
+        ops.linear_fwd(f1, pk.w2[i], layer.mlp.fc2.bias, out)                           # branch; added by the next LayerNorm
+        return x1, out, saved
+    ops.linear_fwd(f1, pk.w2[i], layer.mlp.fc2.bias, out, residual=x1, ldr=C_)
+    return out, None, saved
+
+
+def _pooled_ln(x, pend, rmap, ln, B: int, C_: int, eps: float):
+    """LayerNorm of B selected rows (CLS / EOS, picked by `rmap`) of the final hidden state x (+ pend) -> (pooled bf16 [B, C],
+    mean, rstd, (saved LayerNorm input, its row map))."""
+    dev = x.device
+    plain = ops.rowmap(C_)
+    pooled = torch.empty(B, C_, dtype=bf16, device=dev)
+    mean = torch.empty(B, dtype=f32, device=dev); rstd = torch.empty_like(mean)
+    if pend is None:
+        ops.layernorm_fwd(x, rmap, pooled, plain, ln.weight, ln.bias, mean, rstd, B, C_, eps)
+        return pooled, mean, rstd, (x, rmap)
+    rows_in = torch.empty(B, C_, dtype=f32, device=dev)
+    ops.layernorm_fwd(x, rmap, pooled, plain, ln.weight, ln.bias, mean, rstd, B, C_, eps, add=pend, addmap=rmap, sum_out=rows_in,
+                      summap=plain)
+    return pooled, mean, rstd, (rows_in, plain)
 
 
 def _colsum(x: torch.Tensor, out: torch.Tensor, aux) -> None:
@@ -420,7 +464,8 @@ def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
     gmap = ops.rowmap(C_, group=M, group_stride=S * C_)
     mean0p = torch.empty(B * T * L, dtype=f32, device=dev); rstd0p = torch.empty_like(mean0p)
     mean0g = torch.empty(B * M, dtype=f32, device=dev); rstd0g = torch.empty_like(mean0g)
-    x = torch.empty(rows, C_, dtype=bf16, device=dev)
+    fp32res = _residual_fp32(model)
+    x = torch.empty(rows, C_, dtype=f32 if fp32res else bf16, device=dev)
     ln0 = vm.pre_layrnorm
     ops.layernorm_fwd(x0, pmap, x, pmap, ln0.weight, ln0.bias, mean0p, rstd0p, B * T * L, C_, eps, x_off=M * C_,
                       y_off=M * C_)
@@ -434,28 +479,28 @@ def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
         return lse
 
     layer_saved = []
+    pend = None
     timer = getattr(model, "block_timer", None)   # bench.py: CUDA events around each ViP block (metric 2 of BASELINE.json)
     for i, layer in enumerate(vm.encoder.layers):
         if timer is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        x, sv = _layer_fwd(x, layer, pk, i, eps, attn_fwd, rows, save)
+        x, pend, sv = _layer_fwd(x, pend, layer, pk, i, eps, attn_fwd, rows, save, fp32res)
         if timer is not None:
             e1.record()
             timer.append(("fwd", e0, e1))
         layer_saved.append(sv)
     # pooled = post_layernorm(last_hidden[:, 0])  (CLIP_ViP.py:891-893): CLS rows picked by the row map
     cls_map = ops.rowmap(C_, group=1, group_stride=S * C_)
-    pooled = torch.empty(B, C_, dtype=bf16, device=dev)
-    meanp = torch.empty(B, dtype=f32, device=dev); rstdp = torch.empty_like(meanp)
-    ops.layernorm_fwd(x, cls_map, pooled, plain, vm.post_layernorm.weight, vm.post_layernorm.bias, meanp, rstdp, B, C_, eps)
+    pooled, meanp, rstdp, post_in = _pooled_ln(x, pend, cls_map, vm.post_layernorm, B, C_, eps)
     wproj = _small_bf16(model, "vproj", model.visual_projection.weight)
     proj = torch.empty(B, cfg.projection_dim, dtype=f32, device=dev)
     ops.linear_fwd(pooled, wproj, None, proj, out_mode=_lib.OUT_F32)
     saved = None
     if save:
         saved = SimpleNamespace(B=B, T=T, S=S, rows=rows, patches=patches, x0=x0, stats0=(mean0p, rstd0p, mean0g, rstd0g),
-                                layers=layer_saved, x_last=x, pooled=pooled, meanp=meanp, rstdp=rstdp, ws=ws)
+                                layers=layer_saved, x_last=(x, pend), post_in=post_in, pooled=pooled, meanp=meanp, rstdp=rstdp,
+                                ws=ws)
     return proj, saved
 
 
@@ -475,8 +520,8 @@ def _vision_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str,
     ops.linear_dgrad(dproj_bf16, wproj, dpooled)
     dx = torch.zeros(rows, C_, dtype=bf16, device=dev)  # only the CLS rows receive gradient from the head
     cls_map = ops.rowmap(C_, group=1, group_stride=S * C_)
-    ops.layernorm_bwd(dpooled, plain, sv.x_last, cls_map, vm.post_layernorm.weight, sv.meanp, sv.rstdp, None, None, dx,
-                      cls_map, grads["vision_model.post_layernorm.weight"], grads["vision_model.post_layernorm.bias"], B, C_)
+    ops.layernorm_bwd(dpooled, plain, sv.post_in[0], sv.post_in[1], vm.post_layernorm.weight, sv.meanp, sv.rstdp, None, None,
+                      dx, cls_map, grads["vision_model.post_layernorm.weight"], grads["vision_model.post_layernorm.bias"], B, C_)
 
     delta = torch.empty(B, H, S, dtype=f32, device=dev)       # rowsum(dO * O), scratch of the attention backward
 
@@ -542,24 +587,24 @@ def _text_fwd(model: CLIPModel, input_ids: torch.Tensor, attention_mask: Optiona
         return probs
 
     layer_saved = []
+    pend = None
+    fp32res = _residual_fp32(model)
     for i, layer in enumerate(tm.encoder.layers):
-        x, sv = _layer_fwd(x, layer, pk, i, eps, attn_fwd, rows, save)
+        x, pend, sv = _layer_fwd(x, pend, layer, pk, i, eps, attn_fwd, rows, save, fp32res)
         layer_saved.append(sv)
     # final_layer_norm is per-row, so it is applied to the pooled EOS row only (first argmax of the ids, :776)
     eos = torch.empty(B, dtype=torch.int64, device=dev)
     ops.eos_offsets(ids, eos, None, C_)
     plain = ops.rowmap(C_)
     emap = ops.rowmap(C_, offsets=eos)
-    pooled = torch.empty(B, C_, dtype=bf16, device=dev)
-    meanp = torch.empty(B, dtype=f32, device=dev); rstdp = torch.empty_like(meanp)
-    ops.layernorm_fwd(x, emap, pooled, plain, tm.final_layer_norm.weight, tm.final_layer_norm.bias, meanp, rstdp, B, C_, eps)
+    pooled, meanp, rstdp, post_in = _pooled_ln(x, pend, emap, tm.final_layer_norm, B, C_, eps)
     wproj = _small_bf16(model, "tproj", model.text_projection.weight)
     proj = torch.empty(B, cfg.projection_dim, dtype=f32, device=dev)
     ops.linear_fwd(pooled, wproj, None, proj, out_mode=_lib.OUT_F32)
     saved = None
     if save:
-        saved = SimpleNamespace(B=B, Lt=Lt, rows=rows, ids=ids, layers=layer_saved, x_last=x, eos=eos, pooled=pooled,
-                                meanp=meanp, rstdp=rstdp, err=err)
+        saved = SimpleNamespace(B=B, Lt=Lt, rows=rows, ids=ids, layers=layer_saved, x_last=(x, pend), post_in=post_in, eos=eos,
+                                pooled=pooled, meanp=meanp, rstdp=rstdp, err=err)
     return proj, saved
 
 
@@ -577,8 +622,8 @@ def _text_bwd(model: CLIPModel, dproj_bf16: torch.Tensor, sv, grads: Dict[str, t
     ops.linear_dgrad(dproj_bf16, wproj, dpooled)
     dx = torch.zeros(rows, C_, dtype=bf16, device=dev)
     emap = ops.rowmap(C_, offsets=sv.eos)
-    ops.layernorm_bwd(dpooled, plain, sv.x_last, emap, tm.final_layer_norm.weight, sv.meanp, sv.rstdp, None, None, dx, emap,
-                      grads["text_model.final_layer_norm.weight"], grads["text_model.final_layer_norm.bias"], B, C_)
+    ops.layernorm_bwd(dpooled, plain, sv.post_in[0], sv.post_in[1], tm.final_layer_norm.weight, sv.meanp, sv.rstdp, None, None,
+                      dx, emap, grads["text_model.final_layer_norm.weight"], grads["text_model.final_layer_norm.bias"], B, C_)
 
     def attn_bwd(qkv, a, da, probs, dqkv):
         ops.text_attention_bwd(qkv, da, probs, dqkv, B, H, Lt, C_, pk.q_scale)
