@@ -68,8 +68,11 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void spin_guard(long long t0, const char* what) {
-  if (clock64() - t0 > XP_WAIT_TIMEOUT_CYCLES) {
+// Ranks reach the exchange at different times (a slow rank's forward, the first step's lazy initialisation): the flag wait
+// tolerates ~60 s of skew before it traps; the intra-GPU waits keep the library-wide 4 s limit.
+constexpr long long NF_PEER_TIMEOUT_CYCLES = 120000000000ll;
+__device__ __forceinline__ void spin_guard(long long t0, const char* what, long long limit = XP_WAIT_TIMEOUT_CYCLES) {
+  if (clock64() - t0 > limit) {
     printf("xpretrain_b200: nce_gather_fused timeout waiting for %s (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
     __trap();
   }
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(NF_THREADS, 1) nce_gather_fused_kernel(const N
     if (tid < p.world) {
       const unsigned int* flag = reinterpret_cast<const unsigned int*>(own) + tid;
       const long long t0 = clock64();
-      while (static_cast<int>(ld_acquire_sys(flag) - p.epoch) < 0) spin_guard(t0, "a peer's epoch flag");
+      while (static_cast<int>(ld_acquire_sys(flag) - p.epoch) < 0) spin_guard(t0, "a peer's epoch flag", NF_PEER_TIMEOUT_CYCLES);
     }
   }
   tc_fence_before();
