@@ -339,15 +339,14 @@ extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float
 }
 
 // =====================================================================================================
-// Backward (round 2: software-pipelined).  Persistent, one CTA per SM, 20 warps:
+// Backward (round 2: software-pipelined).  Persistent, one CTA per SM, 18 warps:
 //   warp 0        TMA producer (one thread): per item, five independently released operand groups —
 //                 K' (+global keys; DOUBLE-buffered across items), Q'/dO' rows [0,128) ("q0"), Q'/dO' rows [128,L) + the
 //                 M global rows ("q1"), V' keys [0,128) ("v0"), V' keys [128,L) + global ("v1") — so that the next item's
 //                 first step is already staged while the current item's last steps run
-//   warp 1        MMA issuer (one thread)
-//   warp 2        TMEM allocator
-//   warps 4-19    four math warpgroups; thread = query row (TMEM lane) of the current 128-row query tile, warpgroup g
-//                 owns key columns [32g, 32g+32) of the step
+//   warp 1        MMA issuer (one thread); also allocates / frees TMEM
+//   warps 2-17    four math warpgroups; thread = query row (TMEM lane = 32 (warp % 4) + lane) of the current 128-row query
+//                 tile, warpgroup g = (warp - 2) / 4 owns key columns [32g, 32g+32) of the step
 // An item = (batch b, head h, frame t) = 2 key tiles x 2 query tiles = 4 steps of [128 q x 128 keys] (s = 2 i + j):
 //   S  = Q_j K_i^T, dP = dO_j V_i^T                (tcgen05.mma SS -> TMEM columns [0,128), [128,256))
 //   phase 1: P = exp(S - lse) kept as packed bf16 in REGISTERS -> the S columns are released at once, so S of step
@@ -363,7 +362,7 @@ extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float
 // delta_i = sum_d dO_id O_id is precomputed (vip_attn_delta_kernel).  The gradients of the M global rows are emitted as
 // per-frame fp32 partials and reduced by vip_attn_bwd_combine (vip_attention.cu).
 constexpr int TB_MATH_WARPS = 16;
-constexpr int TB_THREADS = (4 + TB_MATH_WARPS) * 32;       // 640
+constexpr int TB_THREADS = (2 + TB_MATH_WARPS) * 32;       // 576: <= 112 registers per thread
 constexpr int TB_KBUF = (TC_FK + TC_GK) * 128;             // one K' or V' buffer: [208 frame + 16 global rows][128 B]
 constexpr int TB_SQ = 0;                                   // [256][128 B]
 constexpr int TB_SDO = TB_SQ + 256 * 128;                  // [256][128 B]
@@ -442,7 +441,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
     for (int i = 0; i < TB_NBAR; ++i) mbar_init(&bar[i], (i == S_FREE || i == PDS_READY) ? TB_MATH_WARPS : 1);
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -501,33 +500,37 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
       constexpr uint32_t id_s16 = make_idesc_bf16(128, 16, 0, 0);
       constexpr uint32_t id_kv = make_idesc_bf16(128, TC_HD, 1, 1);   // A = P / dS MN-major, B = dO / Q MN-major
       constexpr uint32_t id_q = make_idesc_bf16(128, TC_HD, 0, 1);    // A = dS K-major, B = K MN-major
-      const uint32_t sQ = base + TB_SQ, sdO = base + TB_SDO, sV = base + TB_SV, sVg = sV + TC_FK * 128,
-                     sP = base + TB_SP, sdS = base + TB_SDS;
+      // One thread issues ~60 MMAs per step: descriptors are built ONCE (a descriptor of the same layout at +x bytes is the
+      // base descriptor + (x >> 4): the 14-bit start-address field never overflows inside the 227 KB of shared memory), so
+      // an MMA costs one 64-bit add per operand instead of a shift / mask / or chain.
+      auto at = [](uint64_t desc, uint32_t byte_off) { return desc + (byte_off >> 4); };
+      const uint64_t q_k = make_smem_desc_sw128(base + TB_SQ, 16, 1024), o_k = make_smem_desc_sw128(base + TB_SDO, 16, 1024);
+      const uint64_t q_m = make_smem_desc_sw128(base + TB_SQ, 16384, 1024), o_m = make_smem_desc_sw128(base + TB_SDO, 16384, 1024);
+      const uint64_t p_m = make_smem_desc_sw128(base + TB_SP, 16384, 1024), s_m = make_smem_desc_sw128(base + TB_SDS, 16384, 1024);
+      const uint64_t s_k = make_smem_desc_sw128(base + TB_SDS, 16, 1024);
+      const uint64_t v_k = make_smem_desc_sw128(base + TB_SV, 16, 1024);
+      const uint64_t k_k0 = make_smem_desc_sw128(base + TB_SK, 16, 1024), k_m0 = make_smem_desc_sw128(base + TB_SK, 16384, 1024);
       // the three gradient products of step (i, j) with K' in buffer kb
       auto issue_grads = [&](int i, int j, int kb) {
         if (dbg & 1) return;
-        const uint32_t sK = base + TB_SK + kb * TB_KBUF, sKg = sK + TC_FK * 128;
+        const uint64_t k_m = at(k_m0, kb * TB_KBUF);
+        const uint64_t ob = at(o_m, j * 16384), qb = at(q_m, j * 16384);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {   // K = the 128 query rows of tile j
           const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-          umma_bf16(tdV, make_smem_desc_sw128(sP + ks * 2048, 16384, 1024),
-                    make_smem_desc_sw128(sdO + j * 16384 + ks * 2048, 16384, 1024), id_kv, acc);
-          umma_bf16(tdK, make_smem_desc_sw128(sdS + ks * 2048, 16384, 1024),
-                    make_smem_desc_sw128(sQ + j * 16384 + ks * 2048, 16384, 1024), id_kv, acc);
+          umma_bf16(tdV, at(p_m, ks * 2048), at(ob, ks * 2048), id_kv, acc);
+          umma_bf16(tdK, at(s_m, ks * 2048), at(qb, ks * 2048), id_kv, acc);
         }
         const uint32_t tq = tdQ + j * 64;
         if (i == 0) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)   // K = frame keys [0,128): atom ks/4, 32 B per k-step inside it
-            umma_bf16(tq, make_smem_desc_sw128(sdS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(sK + ks * 2048, 16384, 1024), id_q, ks > 0 ? 1u : 0u);
+            umma_bf16(tq, at(s_k, (ks >> 2) * 16384 + (ks & 3) * 32), at(k_m, ks * 2048), id_q, ks > 0 ? 1u : 0u);
         } else {
 #pragma unroll
           for (int ks = 0; ks < 5; ++ks)   // frame keys [128,208)
-            umma_bf16(tq, make_smem_desc_sw128(sdS + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(sK + (128 + ks * 16) * 128, 16384, 1024), id_q, 1u);
-          umma_bf16(tq, make_smem_desc_sw128(sdS + 16384 + 32, 16, 1024),   // columns [80,96): the global keys
-                    make_smem_desc_sw128(sKg, 16384, 1024), id_q, 1u);
+            umma_bf16(tq, at(s_k, (ks >> 2) * 16384 + (ks & 3) * 32), at(k_m, (128 + ks * 16) * 128), id_q, 1u);
+          umma_bf16(tq, at(s_k, 16384 + 32), at(k_m, TC_FK * 128), id_q, 1u);   // columns [80,96): the global keys
         }
       };
       int n = 0;
@@ -535,7 +538,8 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
       for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
         const int kb = n & 1;
         const uint32_t pi = n & 1, pk = (n >> 1) & 1;
-        const uint32_t sK = base + TB_SK + kb * TB_KBUF, sKg = sK + TC_FK * 128;
+        const uint64_t k_k = at(k_k0, kb * TB_KBUF);
+#pragma unroll
         for (int s = 0; s < 4; ++s, ++step) {
           const int i = s >> 1, j = s & 1;
           // ---- S_n = Q_j K_i^T
@@ -547,15 +551,17 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
           }
           if (step > 0) mbar_wait(&bar[S_FREE], (step - 1) & 1);      // phase 1 of the previous step has read its S
           tc_fence_after();
+          if (!(dbg & 1)) {
 #pragma unroll
-          for (int ks = 0; ks < ((dbg & 1) ? 0 : 4); ++ks) {
-            const uint64_t aq = make_smem_desc_sw128(sQ + j * 16384 + ks * 32, 16, 1024);
-            const uint32_t acc = ks > 0 ? 1u : 0u;
-            if (i == 0) {
-              umma_bf16(tS, aq, make_smem_desc_sw128(sK + ks * 32, 16, 1024), id_s128, acc);
-            } else {
-              umma_bf16(tS, aq, make_smem_desc_sw128(sK + 128 * 128 + ks * 32, 16, 1024), id_s80, acc);
-              umma_bf16(tS + 80, aq, make_smem_desc_sw128(sKg + ks * 32, 16, 1024), id_s16, acc);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t aq = at(q_k, j * 16384 + ks * 32);
+              const uint32_t acc = ks > 0 ? 1u : 0u;
+              if (i == 0) {
+                umma_bf16(tS, aq, at(k_k, ks * 32), id_s128, acc);
+              } else {
+                umma_bf16(tS, aq, at(k_k, 128 * 128 + ks * 32), id_s80, acc);
+                umma_bf16(tS + 80, aq, at(k_k, TC_FK * 128 + ks * 32), id_s16, acc);
+              }
             }
           }
           umma_commit(&bar[S_READY]);
@@ -567,15 +573,17 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
             fence_proxy_async_smem();
           }
           tc_fence_after();
+          if (!(dbg & 1)) {
 #pragma unroll
-          for (int ks = 0; ks < ((dbg & 1) ? 0 : 4); ++ks) {
-            const uint64_t ao = make_smem_desc_sw128(sdO + j * 16384 + ks * 32, 16, 1024);
-            const uint32_t acc = ks > 0 ? 1u : 0u;
-            if (i == 0) {
-              umma_bf16(tdP, ao, make_smem_desc_sw128(sV + ks * 32, 16, 1024), id_s128, acc);
-            } else {
-              umma_bf16(tdP, ao, make_smem_desc_sw128(sV + 128 * 128 + ks * 32, 16, 1024), id_s80, acc);
-              umma_bf16(tdP + 80, ao, make_smem_desc_sw128(sVg + ks * 32, 16, 1024), id_s16, acc);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ao = at(o_k, j * 16384 + ks * 32);
+              const uint32_t acc = ks > 0 ? 1u : 0u;
+              if (i == 0) {
+                umma_bf16(tdP, ao, at(v_k, ks * 32), id_s128, acc);
+              } else {
+                umma_bf16(tdP, ao, at(v_k, 128 * 128 + ks * 32), id_s80, acc);
+                umma_bf16(tdP + 80, ao, at(v_k, TC_FK * 128 + ks * 32), id_s16, acc);
+              }
             }
           }
           umma_commit(&bar[DP_READY]);
@@ -602,9 +610,9 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         umma_commit(&bar[G_DONE]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 2) {
     // ------------------------------------------------------------------------- math warpgroups
-    const int wg = (warp - 4) >> 2;               // key columns [32 wg, 32 wg + 32) of a step
+    const int wg = (warp - 2) >> 2;               // key columns [32 wg, 32 wg + 32) of a step
     const int wq = warp & 3;                       // TMEM lane quarter
     const int trow = wq * 32 + lane;               // TMEM lane == row of the current query tile
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
@@ -670,7 +678,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
       const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
       const long long tok_g = static_cast<long long>(b) * d.S, tok_f = tok_g + d.M + static_cast<long long>(t) * d.L;
       const int j = wg >> 1, half = wg & 1;
-      if (!warp_live[j]) return;
+      if (!(j ? warp_live[1] : warp_live[0])) return;
       const int row = j * 128 + trow;
       uint32_t o[32];
       tmem_ld32(tdQ + j * 64 + half * 32 + lane_off, o);
@@ -708,7 +716,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         const int row = j * 128 + trow;
         const bool q_glob = row >= TC_GROW && row < TC_GROW + d.M;
         const bool cols_on = i == 0 ? (wg * 32 < d.L) : (wg < 3);
-        const bool active = warp_live[j] && cols_on && !(dbg & 2);
+        const bool active = (j ? warp_live[1] : warp_live[0]) && cols_on && !(dbg & 2);
         const uint32_t mask = tb_col_mask(i, wg, d.L, d.M, q_glob && t != 0);
         // ---- phase 1: P = exp(S - lse) -> packed bf16 in registers
         uint32_t ppk[16];
@@ -723,7 +731,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[S_FREE]);     // S is in registers: the tensor pipe may overwrite it
-          const float nl = -l2[j];
+          const float nl = -(j ? l2[1] : l2[0]);
           if (mask == 0xffffffffu) {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
@@ -745,6 +753,28 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[S_FREE]);
         }
+        // ---- phase 2a: dS = P * (dP - delta) into registers.  dP of this step was issued before the previous step's gradient
+        //      products, so it is ready long before they retire: everything but the shared-memory stores stays off the
+        //      G_DONE -> PDS_READY critical chain
+        uint32_t dkp[16];
+        mbar_wait(&bar[DP_READY], step & 1);
+        tc_fence_after();
+        if (active) {
+          uint32_t r[2][16];
+          tmem_ld16(tdP + lane_off + wg * 32, r[0]);
+          tmem_ld16(tdP + lane_off + wg * 32 + 16, r[1]);
+          tmem_ld_wait16(r[0]);
+          tmem_ld_wait16(r[1]);
+          const float dlj = j ? dl[1] : dl[0];
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t pw = ppk[c * 8 + e];
+              dkp[c * 8 + e] = pack_bf16(bf16_lo(pw) * (__uint_as_float(r[c][2 * e]) - dlj),
+                                         bf16_hi(pw) * (__uint_as_float(r[c][2 * e + 1]) - dlj));
+            }
+        }
         // ---- the previous step's gradient products have retired: its P / dS tiles are free, its accumulators final
         if (step > 0) {
           mbar_wait(&bar[G_DONE], (step - 1) & 1);
@@ -755,34 +785,19 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
             drain_q(prev_prob);
           }
         }
-        // ---- phase 2: dS = P * (dP - delta); stage P and dS for the gradient products
-        mbar_wait(&bar[DP_READY], step & 1);
-        tc_fence_after();
+        // ---- phase 2b: stage P and dS for this step's gradient products
         if (active) {
-          uint32_t r[2][16];
-          tmem_ld16(tdP + lane_off + wg * 32, r[0]);
-          tmem_ld16(tdP + lane_off + wg * 32 + 16, r[1]);
-          tmem_ld_wait16(r[0]);
-          tmem_ld_wait16(r[1]);
-          const float dlj = dl[j];
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            uint32_t dk[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const uint32_t pw = ppk[c * 8 + e];
-              dk[e] = pack_bf16(bf16_lo(pw) * (__uint_as_float(r[c][2 * e]) - dlj),
-                                bf16_hi(pw) * (__uint_as_float(r[c][2 * e + 1]) - dlj));
-            }
             const int ch = chunk0 + c * 2;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sPw, trow, ch)), "r"(ppk[c * 8 + 0]),
                          "r"(ppk[c * 8 + 1]), "r"(ppk[c * 8 + 2]), "r"(ppk[c * 8 + 3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sPw, trow, ch + 1)), "r"(ppk[c * 8 + 4]),
                          "r"(ppk[c * 8 + 5]), "r"(ppk[c * 8 + 6]), "r"(ppk[c * 8 + 7]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdSw, trow, ch)), "r"(dk[0]), "r"(dk[1]),
-                         "r"(dk[2]), "r"(dk[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdSw, trow, ch + 1)), "r"(dk[4]), "r"(dk[5]),
-                         "r"(dk[6]), "r"(dk[7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdSw, trow, ch)), "r"(dkp[c * 8 + 0]),
+                         "r"(dkp[c * 8 + 1]), "r"(dkp[c * 8 + 2]), "r"(dkp[c * 8 + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(sdSw, trow, ch + 1)), "r"(dkp[c * 8 + 4]),
+                         "r"(dkp[c * 8 + 5]), "r"(dkp[c * 8 + 6]), "r"(dkp[c * 8 + 7]) : "memory");
           }
           fence_proxy_async_smem();
         }
@@ -801,7 +816,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
