@@ -14,9 +14,11 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-EMB_REL_L2 = 1.6e-2      # 2 x the reference's own bf16 deviation on the text tower
+# Small-golden bars.  Calibrated on this pool's B200 (profiles/r02_pytest_gpu_parity_v2_fp32_residual.log): the reference's own
+# bf16-autocast run deviates from its fp32 output by 3.8e-3 (video) / 7.7e-3 (text) at full depth; ours by 3.6e-3 / 7.3e-3.
+EMB_REL_L2 = 1.2e-2      # 1.5 x the reference's bf16 deviation of the text tower (the larger one)
 ROW_COSINE = 1.0 - 1e-3
-LOSS_REL = 1e-2          # loss = CE at logit scale ~100: a 4e-3 embedding error moves logits by ~0.1
+LOSS_REL = 1e-2          # a 2..4-pair loss at logit scale ~100 is one sample of the logits error (see _assert_calibrated)
 GRAD_COSINE = 0.97
 
 
@@ -173,14 +175,19 @@ def _full12_case(dev, golden_dir, pad_to):
 
 
 def _assert_calibrated(ours, ref):
-    # Features / logits / gradients: full tensors, so the ratio is statistically meaningful.  Bar: 1.5 x the all-bf16 run of
-    # the reference algorithm (bf16 residual stream, as ours) and never more than 3 x its autocast run (fp32 residual stream).
+    """Full tensors (features, logits matrix, whole gradient tensors): our deviation from the fp32 reference golden may be at
+    most CALIBRATION = 1.5 x the deviation of the REFERENCE's own bf16 path (autocast: fp32 residual stream, bf16 matmul inputs)
+    on the same inputs on this GPU — tighter than SURVEY.md §8c's 2x.  Measured (profiles/r02_pytest_gpu_parity_v2_fp32_residual.log):
+    features 0.95x, logits 1.24x, gradients 0.93x - 1.29x.  With `residual_fp32=False` (round-1 bf16 stream) the features sit at
+    2.4x and only the all-bf16 bar holds, which is why the fp32 stream is the default."""
+    import os
+    against = "pure" if os.environ.get("XP_RESIDUAL_BF16") == "1" else "autocast"
     for k in ours:
         if k == "loss":
             continue
-        assert ours[k] <= CALIBRATION * ref["pure"][k] + 1e-6, (k, ours[k], ref["pure"][k])
-        assert ours[k] <= 3.0 * ref["autocast"][k] + 1e-6, (k, ours[k], ref["autocast"][k])
-    # the scalar loss is ONE sample of that error: bound it by the calibrated logits error instead of a single ratio
+        assert ours[k] <= CALIBRATION * ref[against][k] + 1e-6, (k, ours[k], ref[against][k])
+    # the scalar loss is ONE sample of the logits error (the reference's own two bf16 runs differ 18x on it): bounded by the
+    # larger of the reference deviations, with a floor of 2e-3
     assert ours["loss"] <= max(CALIBRATION * max(ref["pure"]["loss"], ref["autocast"]["loss"]), 2e-3), (ours["loss"], ref)
 
 
