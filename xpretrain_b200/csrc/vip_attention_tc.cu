@@ -22,6 +22,7 @@
 #include "common.h"
 #include "ptx.cuh"
 #include <cstdlib>
+#include <cstdio>
 
 namespace xp {
 
@@ -423,9 +424,14 @@ __device__ __forceinline__ uint32_t tb_col_mask(int i, int wg, int L, int M, boo
 __global__ void __launch_bounds__(TB_THREADS, 1)
 vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restrict__ lse, const float* __restrict__ delta,
                        __nv_bfloat16* __restrict__ dqkv, float* __restrict__ gpart, const TcDims d, float q_scale,
-                       const int dbg) {
+                       const int dbg, long long* __restrict__ trace) {
   // dbg (profiling only, XP_ATTN_BWD_DEBUG): bit 0 = issue no MMAs (commits only), bit 1 = math warps run the barrier
-  // protocol without their loads / exps / stores — isolates the tensor-pipe time from the math time
+  // protocol without their loads / exps / stores — isolates the tensor-pipe time from the math time; bit 2 = CTA 0 records
+  // clock64() time stamps of its first 24 steps (issuer: 4 per step, math warp 2: 5 per step) into `trace`
+#define TB_TRACE(role, k)                                                                              \
+  do {                                                                                                 \
+    if ((dbg & 4) && blockIdx.x == 0 && step < 24) trace[(role) * 24 * 8 + step * 8 + (k)] = clock64(); \
+  } while (0)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -551,6 +557,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
           }
           if (step > 0) mbar_wait(&bar[S_FREE], (step - 1) & 1);      // phase 1 of the previous step has read its S
           tc_fence_after();
+          TB_TRACE(0, 0);
           if (!(dbg & 1)) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -565,6 +572,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
             }
           }
           umma_commit(&bar[S_READY]);
+          TB_TRACE(0, 1);
           // ---- dP_n = dO_j V_i^T
           if (s == 0) mbar_wait(&bar[V0_FULL], pi);
           else if (s == 2) mbar_wait(&bar[V1_FULL], pi);
@@ -573,6 +581,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
             fence_proxy_async_smem();
           }
           tc_fence_after();
+          TB_TRACE(0, 2);
           if (!(dbg & 1)) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -600,6 +609,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
               umma_commit(&bar[K_FREE + pkb]);
             }
           }
+          TB_TRACE(0, 3);
         }
       }
       if (step > 0) {   // the last step's gradient products
@@ -722,6 +732,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         uint32_t ppk[16];
         mbar_wait(&bar[S_READY], step & 1);
         tc_fence_after();
+        if (warp == 2 && lane == 0) TB_TRACE(1, 0);
         if (active) {
           uint32_t r[2][16];
           tmem_ld16(tS + lane_off + wg * 32, r[0]);
@@ -757,8 +768,10 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         //      products, so it is ready long before they retire: everything but the shared-memory stores stays off the
         //      G_DONE -> PDS_READY critical chain
         uint32_t dkp[16];
+        if (warp == 2 && lane == 0) TB_TRACE(1, 1);
         mbar_wait(&bar[DP_READY], step & 1);
         tc_fence_after();
+        if (warp == 2 && lane == 0) TB_TRACE(1, 2);
         if (active) {
           uint32_t r[2][16];
           tmem_ld16(tdP + lane_off + wg * 32, r[0]);
@@ -776,9 +789,11 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
             }
         }
         // ---- the previous step's gradient products have retired: its P / dS tiles are free, its accumulators final
+        if (warp == 2 && lane == 0) TB_TRACE(1, 3);
         if (step > 0) {
           mbar_wait(&bar[G_DONE], (step - 1) & 1);
           tc_fence_after();
+          if (warp == 2 && lane == 0) TB_TRACE(1, 4);
           if (s == 2) drain_kv(0, prob);
           else if (s == 0) {
             drain_kv(1, prev_prob);
@@ -804,6 +819,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[PDS_READY]);
+        if (warp == 2 && lane == 0) TB_TRACE(1, 5);
       }
       prev_prob = prob;
     }
@@ -861,9 +877,29 @@ extern "C" int xp_vip_attention_bwd_tc_partial(const void* qkv, const void* out,
   if (make_tmap_bf16_2d(&tm.do_b, dout, C, rows, d.ld_o, TC_HD, L2 > 0 ? L2 : 1)) return -1;
   if (make_tmap_bf16_2d(&tm.do_g, dout, C, rows, d.ld_o, TC_HD, M)) return -1;
   static const int dbg = [] { const char* e = getenv("XP_ATTN_BWD_DEBUG"); return e ? atoi(e) : 0; }();
+  static long long* trace = nullptr;
+  if ((dbg & 4) && trace == nullptr) XP_CHECK_CUDA(cudaMalloc(&trace, 2 * 24 * 8 * sizeof(long long)));
+  if (dbg & 4) XP_CHECK_CUDA(cudaMemsetAsync(trace, 0, 2 * 24 * 8 * sizeof(long long), st));
   vip_attn_bwd_tc_kernel<<<grid, TB_THREADS, smem, st>>>(tm, lse, delta, static_cast<__nv_bfloat16*>(dqkv), workspace, d,
-                                                         q_scale, dbg);
+                                                         q_scale, dbg, trace);
   XP_CHECK_LAUNCH("vip_attn_bwd_tc_kernel");
+  if (dbg & 4) {   // profiling only: print CTA 0's step timeline of this launch (cycles relative to the first stamp)
+    static int printed = 0;
+    long long h[2 * 24 * 8];
+    XP_CHECK_CUDA(cudaStreamSynchronize(st));
+    XP_CHECK_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+    if (printed++ == 3) {
+      const long long t0 = h[0];
+      fprintf(stderr, "attn_bwd trace (cycles from t0): issuer [S_FREE ok, S issued, PDS ok, dP+G issued] | math warp 2 [S_READY ok, P1 done, DP ok, dS done, G_DONE ok, PDS arrive]\n");
+      for (int sidx = 0; sidx < 24; ++sidx) {
+        fprintf(stderr, "step %2d: I", sidx);
+        for (int k = 0; k < 4; ++k) fprintf(stderr, " %7lld", h[sidx * 8 + k] ? h[sidx * 8 + k] - t0 : -1);
+        fprintf(stderr, " | M");
+        for (int k = 0; k < 6; ++k) fprintf(stderr, " %7lld", h[24 * 8 + sidx * 8 + k] ? h[24 * 8 + sidx * 8 + k] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return 0;
 }
 
