@@ -345,7 +345,9 @@ extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float
 //                 K' (+global keys; DOUBLE-buffered across items), Q'/dO' rows [0,128) ("q0"), Q'/dO' rows [128,L) + the
 //                 M global rows ("q1"), V' keys [0,128) ("v0"), V' keys [128,L) + global ("v1") — so that the next item's
 //                 first step is already staged while the current item's last steps run
-//   warp 1        MMA issuer (one thread); also allocates / frees TMEM
+//   warp 1        MMA issuer A (one thread): S, dP, dV; also allocates / frees TMEM
+//   warp 18       MMA issuer B (one thread): dK, dQ — the N = 64, K = 16 gradient MMAs take ~32 tensor cycles each but ~45
+//                 cycles to issue from one thread (descriptor moves into uniform registers), so the issue is split in two
 //   warps 2-17    four math warpgroups; thread = query row (TMEM lane = 32 (warp % 4) + lane) of the current 128-row query
 //                 tile, warpgroup g = (warp - 2) / 4 owns key columns [32g, 32g+32) of the step
 // An item = (batch b, head h, frame t) = 2 key tiles x 2 query tiles = 4 steps of [128 q x 128 keys] (s = 2 i + j):
@@ -363,7 +365,7 @@ extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float
 // delta_i = sum_d dO_id O_id is precomputed (vip_attn_delta_kernel).  The gradients of the M global rows are emitted as
 // per-frame fp32 partials and reduced by vip_attn_bwd_combine (vip_attention.cu).
 constexpr int TB_MATH_WARPS = 16;
-constexpr int TB_THREADS = (2 + TB_MATH_WARPS) * 32;       // 576: <= 112 registers per thread
+constexpr int TB_THREADS = (3 + TB_MATH_WARPS) * 32;       // 608: producer, two MMA issuers, 16 math warps
 constexpr int TB_KBUF = (TC_FK + TC_GK) * 128;             // one K' or V' buffer: [208 frame + 16 global rows][128 B]
 constexpr int TB_SQ = 0;                                   // [256][128 B]
 constexpr int TB_SDO = TB_SQ + 256 * 128;                  // [256][128 B]
@@ -444,7 +446,9 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
   const int L1 = d.L < 128 ? d.L : 128, L2 = d.L - L1;
 
   if (tid == 0) {
-    for (int i = 0; i < TB_NBAR; ++i) mbar_init(&bar[i], (i == S_FREE || i == PDS_READY) ? TB_MATH_WARPS : 1);
+    for (int i = 0; i < TB_NBAR; ++i)
+      mbar_init(&bar[i], (i == S_FREE || i == PDS_READY) ? TB_MATH_WARPS
+                         : (i == G_DONE || i == Q0_FREE || i == Q1_FREE || i == K_FREE || i == K_FREE1) ? 2 : 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -498,8 +502,8 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         tma_load_2d(gbase + TB_SV + TC_FK * 128, &tm.qkv_g, &bar[V1_FULL], cv, rg);
       }
     }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || warp == 18) {
+    // ---------------------------------------------------------------------------------- MMA issuers A (warp 1) / B (warp 18)
     if (lane == 0) {
       constexpr uint32_t id_s128 = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t id_s80 = make_idesc_bf16(128, 80, 0, 0);
@@ -521,12 +525,15 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         if (dbg & 1) return;
         const uint64_t k_m = at(k_m0, kb * TB_KBUF);
         const uint64_t ob = at(o_m, j * 16384), qb = at(q_m, j * 16384);
+        if (warp == 1) {                   // issuer A: dV_i += P^T dO_j
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // K = the 128 query rows of tile j
-          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-          umma_bf16(tdV, at(p_m, ks * 2048), at(ob, ks * 2048), id_kv, acc);
-          umma_bf16(tdK, at(s_m, ks * 2048), at(qb, ks * 2048), id_kv, acc);
+          for (int ks = 0; ks < 8; ++ks)   // K = the 128 query rows of tile j
+            umma_bf16(tdV, at(p_m, ks * 2048), at(ob, ks * 2048), id_kv, (j > 0 || ks > 0) ? 1u : 0u);
+          return;
         }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)     // issuer B: dK_i += dS^T Q_j, then dQ_j += dS K_i
+          umma_bf16(tdK, at(s_m, ks * 2048), at(qb, ks * 2048), id_kv, (j > 0 || ks > 0) ? 1u : 0u);
         const uint32_t tq = tdQ + j * 64;
         if (i == 0) {
 #pragma unroll
@@ -539,6 +546,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
           umma_bf16(tq, at(s_k, 16384 + 32), at(k_m, TC_FK * 128), id_q, 1u);   // columns [80,96): the global keys
         }
       };
+      const bool is_a = warp == 1;
       int n = 0;
       uint32_t step = 0;
       for (int prob = blockIdx.x; prob < total; prob += gridDim.x, ++n) {
@@ -548,57 +556,61 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
 #pragma unroll
         for (int s = 0; s < 4; ++s, ++step) {
           const int i = s >> 1, j = s & 1;
-          // ---- S_n = Q_j K_i^T
-          if (s == 0) {
-            mbar_wait(&bar[Q0_FULL], pi);
-            mbar_wait(&bar[K_FULL + kb], pk);
-          } else if (s == 1) {
-            mbar_wait(&bar[Q1_FULL], pi);
-          }
-          if (step > 0) mbar_wait(&bar[S_FREE], (step - 1) & 1);      // phase 1 of the previous step has read its S
-          tc_fence_after();
-          TB_TRACE(0, 0);
-          if (!(dbg & 1)) {
+          // ---- S_n = Q_j K_i^T                                                              (issuer A)
+          if (is_a) {
+            if (s == 0) {
+              mbar_wait(&bar[Q0_FULL], pi);
+              mbar_wait(&bar[K_FULL + kb], pk);
+            } else if (s == 1) {
+              mbar_wait(&bar[Q1_FULL], pi);
+            }
+            if (step > 0) mbar_wait(&bar[S_FREE], (step - 1) & 1);    // phase 1 of the previous step has read its S
+            tc_fence_after();
+            TB_TRACE(0, 0);
+            if (!(dbg & 1)) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t aq = at(q_k, j * 16384 + ks * 32);
-              const uint32_t acc = ks > 0 ? 1u : 0u;
-              if (i == 0) {
-                umma_bf16(tS, aq, at(k_k, ks * 32), id_s128, acc);
-              } else {
-                umma_bf16(tS, aq, at(k_k, 128 * 128 + ks * 32), id_s80, acc);
-                umma_bf16(tS + 80, aq, at(k_k, TC_FK * 128 + ks * 32), id_s16, acc);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t aq = at(q_k, j * 16384 + ks * 32);
+                const uint32_t acc = ks > 0 ? 1u : 0u;
+                if (i == 0) {
+                  umma_bf16(tS, aq, at(k_k, ks * 32), id_s128, acc);
+                } else {
+                  umma_bf16(tS, aq, at(k_k, 128 * 128 + ks * 32), id_s80, acc);
+                  umma_bf16(tS + 80, aq, at(k_k, TC_FK * 128 + ks * 32), id_s16, acc);
+                }
               }
             }
+            umma_commit(&bar[S_READY]);
+            TB_TRACE(0, 1);
+            if (s == 0) mbar_wait(&bar[V0_FULL], pi);
+            else if (s == 2) mbar_wait(&bar[V1_FULL], pi);
           }
-          umma_commit(&bar[S_READY]);
-          TB_TRACE(0, 1);
-          // ---- dP_n = dO_j V_i^T
-          if (s == 0) mbar_wait(&bar[V0_FULL], pi);
-          else if (s == 2) mbar_wait(&bar[V1_FULL], pi);
           if (step > 0) {
             mbar_wait(&bar[PDS_READY], (step - 1) & 1);               // dP of the previous step consumed; its P, dS staged
             fence_proxy_async_smem();
           }
           tc_fence_after();
-          TB_TRACE(0, 2);
-          if (!(dbg & 1)) {
+          // ---- dP_n = dO_j V_i^T                                                             (issuer A)
+          if (is_a) {
+            TB_TRACE(0, 2);
+            if (!(dbg & 1)) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ao = at(o_k, j * 16384 + ks * 32);
-              const uint32_t acc = ks > 0 ? 1u : 0u;
-              if (i == 0) {
-                umma_bf16(tdP, ao, at(v_k, ks * 32), id_s128, acc);
-              } else {
-                umma_bf16(tdP, ao, at(v_k, 128 * 128 + ks * 32), id_s80, acc);
-                umma_bf16(tdP + 80, ao, at(v_k, TC_FK * 128 + ks * 32), id_s16, acc);
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ao = at(o_k, j * 16384 + ks * 32);
+                const uint32_t acc = ks > 0 ? 1u : 0u;
+                if (i == 0) {
+                  umma_bf16(tdP, ao, at(v_k, ks * 32), id_s128, acc);
+                } else {
+                  umma_bf16(tdP, ao, at(v_k, 128 * 128 + ks * 32), id_s80, acc);
+                  umma_bf16(tdP + 80, ao, at(v_k, TC_FK * 128 + ks * 32), id_s16, acc);
+                }
               }
             }
+            umma_commit(&bar[DP_READY]);
+            if (s == 1) umma_commit(&bar[V0_FREE]);
+            else if (s == 3) umma_commit(&bar[V1_FREE]);
           }
-          umma_commit(&bar[DP_READY]);
-          if (s == 1) umma_commit(&bar[V0_FREE]);
-          else if (s == 3) umma_commit(&bar[V1_FREE]);
-          // ---- gradient products of the previous step
+          // ---- gradient products of the previous step: dV (A) | dK, dQ (B); both commit on G_DONE and on the operand frees
           if (step > 0) {
             const int ps = (s + 3) & 3, pkb = s == 0 ? (kb ^ 1) : kb;
             issue_grads(ps >> 1, ps & 1, pkb);
@@ -609,7 +621,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
               umma_commit(&bar[K_FREE + pkb]);
             }
           }
-          TB_TRACE(0, 3);
+          if (is_a) TB_TRACE(0, 3);
         }
       }
       if (step > 0) {   // the last step's gradient products
@@ -648,70 +660,69 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         dl[j] = idx >= 0 ? delta[idx] : 0.f;
       }
     };
-    // dV_i / dK_i: warpgroups 0,1 drain the two 32-column halves of dV, warpgroups 2,3 those of dK; thread = key row
-    auto drain_kv = [&](int i, int prob) {
+    // Accumulator drain.  One warp moves 32 rows x 64 columns of ONE accumulator (acc 0: dV_i, 1: dK_i, 2: dQ_0, 3: dQ_1; rows =
+    // its TMEM lane quarter): TMEM -> registers -> bf16 -> its 4 KB slot of the P / dS tiles (free between G_DONE of the previous
+    // step and this step's phase 2b) -> global stores in which 8 lanes cover one 128-byte row segment.  A lane-per-row store
+    // touches 32 different lines per instruction and cost ~5 k cycles per drain (profiles/r02_attn_bwd_trace.md); this way an
+    // instruction writes 4 full lines.  The M global rows (fp32 per-frame partials) are written by their owning lanes.
+    auto drain = [&](int acc, int i, int prob) {
       const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
       const long long tok_g = static_cast<long long>(b) * d.S, tok_f = tok_g + d.M + static_cast<long long>(t) * d.L;
-      int key = -1, gk = -1;
-      if (i == 0) { if (trow < d.L) key = trow; }
-      else if (trow < 80) { if (128 + trow < d.L) key = 128 + trow; }
-      else if (trow < 80 + d.M) gk = trow - 80;
-      const int r0 = wq * 32;
-      const bool any = i == 0 ? (r0 < d.L) : (r0 < 80 ? (128 + r0 < d.L) || r0 + 31 >= 80 : r0 < 80 + d.M);
+      // accumulator row ar (0..127) -> sequence row of the frame (or -1), and global-token index (or -1)
+      auto frame_row = [&](int ar) {
+        if (acc >= 2) { const int row = (acc - 2) * 128 + ar; return row < d.L ? row : -1; }
+        if (i == 0) return ar < d.L ? ar : -1;
+        return (ar < 80 && 128 + ar < d.L) ? 128 + ar : -1;
+      };
+      auto glob_row = [&](int ar) {
+        if (acc >= 2) { const int row = (acc - 2) * 128 + ar; return (row >= TC_GROW && row < TC_GROW + d.M) ? row - TC_GROW : -1; }
+        return (i == 1 && ar >= 80 && ar < 80 + d.M) ? ar - 80 : -1;
+      };
+      const int ar0 = wq * 32;
+      bool any = false;
+      for (int k = 0; k < 32; ++k) any = any || frame_row(ar0 + k) >= 0 || glob_row(ar0 + k) >= 0;
       if (!any) return;
-      const int which = wg >> 1, half = wg & 1;          // 0: dV, 1: dK
-      uint32_t o[32];
-      tmem_ld32((which == 0 ? tdV : tdK) + lane_off + half * 32, o);
-      tmem_ld_wait(o);
-      const int sect = which == 0 ? 2 : 1;
-      if (key >= 0) {
-        __nv_bfloat16* drow = dqkv + (tok_f + key) * d.ld_qkv + sect * d.C + h * TC_HD + half * 32;
+      const uint32_t tsrc = (acc == 0 ? tdV : acc == 1 ? tdK : tdQ + (acc - 2) * 64) + lane_off;
+      const int sect = acc == 0 ? 2 : (acc == 1 ? 1 : 0);            // [q | k | v] section of dqkv / of the partials
+      const float scale = acc >= 2 ? q_scale : 1.f;
+      const uint32_t slot = base + TB_SP + static_cast<uint32_t>(warp - 2) * 4096u;
+      const int my_g = glob_row(ar0 + lane);
+      float* grow = gpart + (((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M + my_g) * 3 * TC_HD + sect * TC_HD;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o[32];
+        tmem_ld32(tsrc + half * 32, o);
+        tmem_ld_wait(o);
+        if (my_g >= 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(grow + half * 32 + q * 4) = make_float4(__uint_as_float(o[q * 4]), __uint_as_float(o[q * 4 + 1]),
+                                                                                __uint_as_float(o[q * 4 + 2]), __uint_as_float(o[q * 4 + 3]));
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]), __uint_as_float(o[q * 8 + 1]));
-          v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]), __uint_as_float(o[q * 8 + 3]));
-          v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]), __uint_as_float(o[q * 8 + 5]));
-          v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]), __uint_as_float(o[q * 8 + 7]));
-          *reinterpret_cast<uint4*>(drow + q * 8) = v;
+          const uint32_t v0 = pack_bf16(__uint_as_float(o[q * 8 + 0]) * scale, __uint_as_float(o[q * 8 + 1]) * scale);
+          const uint32_t v1 = pack_bf16(__uint_as_float(o[q * 8 + 2]) * scale, __uint_as_float(o[q * 8 + 3]) * scale);
+          const uint32_t v2 = pack_bf16(__uint_as_float(o[q * 8 + 4]) * scale, __uint_as_float(o[q * 8 + 5]) * scale);
+          const uint32_t v3 = pack_bf16(__uint_as_float(o[q * 8 + 6]) * scale, __uint_as_float(o[q * 8 + 7]) * scale);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(slot, lane, half * 4 + q)), "r"(v0), "r"(v1),
+                       "r"(v2), "r"(v3) : "memory");
         }
-      } else if (gk >= 0) {
-        float* grow = gpart + (((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M + gk) * 3 * TC_HD + sect * TC_HD + half * 32;
+      }
+      __syncwarp();
+      const int c = lane & 7;
+      __nv_bfloat16* gcol = dqkv + sect * d.C + h * TC_HD + c * 8;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(grow + q * 4) = make_float4(__uint_as_float(o[q * 4]), __uint_as_float(o[q * 4 + 1]),
-                                                                 __uint_as_float(o[q * 4 + 2]), __uint_as_float(o[q * 4 + 3]));
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);                      // row inside this warp's 32
+        const int fr = frame_row(ar0 + rr);
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sw128(slot, rr, c)) : "memory");
+        if (fr >= 0) *reinterpret_cast<uint4*>(gcol + (tok_f + fr) * d.ld_qkv) = v;
       }
     };
-    // dQ_0 (warpgroups 0,1) / dQ_1 (warpgroups 2,3), 32 columns each; thread = query row
-    auto drain_q = [&](int prob) {
-      const int t = prob % d.T, h = (prob / d.T) % d.H, b = prob / (d.T * d.H);
-      const long long tok_g = static_cast<long long>(b) * d.S, tok_f = tok_g + d.M + static_cast<long long>(t) * d.L;
-      const int j = wg >> 1, half = wg & 1;
-      if (!(j ? warp_live[1] : warp_live[0])) return;
-      const int row = j * 128 + trow;
-      uint32_t o[32];
-      tmem_ld32(tdQ + j * 64 + half * 32 + lane_off, o);
-      tmem_ld_wait(o);
-      if (row < d.L) {
-        __nv_bfloat16* drow = dqkv + (tok_f + row) * d.ld_qkv + h * TC_HD + half * 32;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * q_scale, __uint_as_float(o[q * 8 + 1]) * q_scale);
-          v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * q_scale, __uint_as_float(o[q * 8 + 3]) * q_scale);
-          v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * q_scale, __uint_as_float(o[q * 8 + 5]) * q_scale);
-          v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * q_scale, __uint_as_float(o[q * 8 + 7]) * q_scale);
-          *reinterpret_cast<uint4*>(drow + q * 8) = v;
-        }
-      } else if (row >= TC_GROW && row < TC_GROW + d.M) {
-        float* grow = gpart + (((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M + (row - TC_GROW)) * 3 * TC_HD + half * 32;
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(grow + q * 4) = make_float4(__uint_as_float(o[q * 4]), __uint_as_float(o[q * 4 + 1]),
-                                                                 __uint_as_float(o[q * 4 + 2]), __uint_as_float(o[q * 4 + 3]));
-      }
-    };
+    // 512 math threads: the staging slots alias the P / dS tiles, so nobody may start phase 2b before every drain has been read back
+    auto drain_sync = [] { asm volatile("bar.sync 1, 512;" ::: "memory"); };
 
     float l2n[2], dln[2];
     if (static_cast<int>(blockIdx.x) < total) load_stats(blockIdx.x, l2n, dln);
@@ -794,10 +805,12 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
           mbar_wait(&bar[G_DONE], (step - 1) & 1);
           tc_fence_after();
           if (warp == 2 && lane == 0) TB_TRACE(1, 4);
-          if (s == 2) drain_kv(0, prob);
-          else if (s == 0) {
-            drain_kv(1, prev_prob);
-            drain_q(prev_prob);
+          if (s == 2) {                         // key tile 0 of this item is complete: dV_0 / dK_0
+            if (wg < 2) drain(wg, 0, prob);
+            drain_sync();
+          } else if (s == 0) {                  // the previous item is complete: dV_1 / dK_1 / dQ_0 / dQ_1, one per warpgroup
+            drain(wg, 1, prev_prob);
+            drain_sync();
           }
         }
         // ---- phase 2b: stage P and dS for this step's gradient products
@@ -826,8 +839,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
     if (step > 0) {   // accumulators of the last item
       mbar_wait(&bar[G_DONE], (step - 1) & 1);
       tc_fence_after();
-      drain_kv(1, prev_prob);
-      drain_q(prev_prob);
+      drain(wg, 1, prev_prob);
     }
   }
   tc_fence_before();
