@@ -190,6 +190,7 @@ vip_attn_fwd_tc_kernel(const __grid_constant__ TfMaps tm, __nv_bfloat16* __restr
     const bool is_frame = row < d.L;
     const bool is_glob = row >= TC_GROW && row < TC_GROW + d.M;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + j * 256;
+    const uint32_t stage = buf0 + 2 * TC_BUF_BYTES + 1024 + static_cast<uint32_t>(warp - 4) * 4096u;   // output staging, 4 KB per warp
     // a warp whose 32 rows hold neither frame nor global queries only takes part in the barrier protocol
     const bool warp_active = (j * 128 + wq * 32 < d.L) || (j * 128 + wq * 32 + 31 >= TC_GROW && j * 128 + wq * 32 < TC_GROW + d.M);
     int n = 0;
@@ -261,7 +262,6 @@ vip_attn_fwd_tc_kernel(const __grid_constant__ TfMaps tm, __nv_bfloat16* __restr
       tc_fence_after();
       const long long srow = d.M + static_cast<long long>(t) * d.L + row;      // position in the sequence
       float* gp = part + (((static_cast<long long>(b) * d.H + h) * d.T + t) * d.M + (row - TC_GROW)) * 66;
-      __nv_bfloat16* dst = out + (static_cast<long long>(b) * d.S + srow) * d.ld_o + h * TC_HD;
       const float inv = 1.f / sum;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -277,17 +277,34 @@ vip_attn_fwd_tc_kernel(const __grid_constant__ TfMaps tm, __nv_bfloat16* __restr
         if (is_glob) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) gp[2 + half * 32 + i] = __uint_as_float(o[i]);
-        } else if (is_frame) {
+        }
+        if (warp_active) {      // bf16 rows into this warp's 4 KB staging slot (dead rows: finite garbage, never stored)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
-            v.y = pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
-            v.z = pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
-            v.w = pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + half * 32 + q * 8) = v;
+            const uint32_t v0 = pack_bf16(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+            const uint32_t v1 = pack_bf16(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+            const uint32_t v2 = pack_bf16(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+            const uint32_t v3 = pack_bf16(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw128(stage, lane, half * 4 + q)), "r"(v0), "r"(v1),
+                         "r"(v2), "r"(v3) : "memory");
           }
         }
+      }
+      // coalesced output: 8 lanes cover one 128-byte row, an instruction writes 4 full lines (a lane-per-row store would touch
+      // 32 lines per instruction and serialise in the LSU)
+      if (warp_active) {
+        __syncwarp();
+        const int c = lane & 7;
+        __nv_bfloat16* obase = out + (static_cast<long long>(b) * d.S + d.M + static_cast<long long>(t) * d.L) * d.ld_o + h * TC_HD + c * 8;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const int frow = j * 128 + wq * 32 + rr;              // row within sQ; frame rows are [0, L)
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sw128(stage, rr, c)) : "memory");
+          if (frow < d.L) *reinterpret_cast<uint4*>(obase + static_cast<long long>(frow) * d.ld_o) = v;
+        }
+        __syncwarp();
       }
       if (is_glob) {
         gp[0] = mx;
@@ -320,7 +337,7 @@ extern "C" int xp_vip_attention_fwd_tc_partial(const void* qkv, void* out, float
   d.S = static_cast<long long>(M) + static_cast<long long>(T) * L;
   d.ld_qkv = 3LL * C;
   d.ld_o = C;
-  const int smem = 2 * TC_BUF_BYTES + 1024 + 128;
+  const int smem = 2 * TC_BUF_BYTES + 1024 + 1024 + 8 * 4096;     // two operand buffers, barriers, alignment slack, output staging
   static bool attr = false;
   if (!attr) {
     XP_CHECK_CUDA(cudaFuncSetAttribute(vip_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -660,6 +677,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         dl[j] = idx >= 0 ? delta[idx] : 0.f;
       }
     };
+    uint32_t step = 0;
     // Accumulator drain.  One warp moves 32 rows x 64 columns of ONE accumulator (acc 0: dV_i, 1: dK_i, 2: dQ_0, 3: dQ_1; rows =
     // its TMEM lane quarter): TMEM -> registers -> bf16 -> its 4 KB slot of the P / dS tiles (free between G_DONE of the previous
     // step and this step's phase 2b) -> global stores in which 8 lanes cover one 128-byte row segment.  A lane-per-row store
@@ -679,8 +697,10 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         return (i == 1 && ar >= 80 && ar < 80 + d.M) ? ar - 80 : -1;
       };
       const int ar0 = wq * 32;
-      bool any = false;
-      for (int k = 0; k < 32; ++k) any = any || frame_row(ar0 + k) >= 0 || glob_row(ar0 + k) >= 0;
+      // this warp's 32 rows hold a live frame row iff the first one is live (live rows are a prefix), or a global row
+      const bool any = frame_row(ar0) >= 0 ||
+                       (acc >= 2 ? (acc == 3 && ar0 + 31 >= TC_GROW - 128 && ar0 < TC_GROW - 128 + d.M)
+                                 : (i == 1 && ar0 + 31 >= 80 && ar0 < 80 + d.M));
       if (!any) return;
       const uint32_t tsrc = (acc == 0 ? tdV : acc == 1 ? tdK : tdQ + (acc - 2) * 64) + lane_off;
       const int sect = acc == 0 ? 2 : (acc == 1 ? 1 : 0);            // [q | k | v] section of dqkv / of the partials
@@ -710,6 +730,7 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         }
       }
       __syncwarp();
+      if (warp == 2 && lane == 0) TB_TRACE(1, 6);
       const int c = lane & 7;
       __nv_bfloat16* gcol = dqkv + sect * d.C + h * TC_HD + c * 8;
 #pragma unroll
@@ -720,13 +741,13 @@ vip_attn_bwd_tc_kernel(const __grid_constant__ TbMaps tm, const float* __restric
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sw128(slot, rr, c)) : "memory");
         if (fr >= 0) *reinterpret_cast<uint4*>(gcol + (tok_f + fr) * d.ld_qkv) = v;
       }
+      if (warp == 2 && lane == 0) TB_TRACE(1, 7);
     };
     // 512 math threads: the staging slots alias the P / dS tiles, so nobody may start phase 2b before every drain has been read back
     auto drain_sync = [] { asm volatile("bar.sync 1, 512;" ::: "memory"); };
 
     float l2n[2], dln[2];
     if (static_cast<int>(blockIdx.x) < total) load_stats(blockIdx.x, l2n, dln);
-    uint32_t step = 0;
     int prev_prob = -1;
     for (int prob = blockIdx.x; prob < total; prob += gridDim.x) {
       const int t = prob % d.T;
@@ -902,12 +923,12 @@ extern "C" int xp_vip_attention_bwd_tc_partial(const void* qkv, const void* out,
     XP_CHECK_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
     if (printed++ == 3) {
       const long long t0 = h[0];
-      fprintf(stderr, "attn_bwd trace (cycles from t0): issuer [S_FREE ok, S issued, PDS ok, dP+G issued] | math warp 2 [S_READY ok, P1 done, DP ok, dS done, G_DONE ok, PDS arrive]\n");
+      fprintf(stderr, "attn_bwd trace (cycles from t0): issuer [S_FREE ok, S issued, PDS ok, dP+G issued] | math warp 2 [S_READY ok, P1 done, DP ok, dS done, G_DONE ok, PDS arrive, drain staged, drain stored]\n");
       for (int sidx = 0; sidx < 24; ++sidx) {
         fprintf(stderr, "step %2d: I", sidx);
         for (int k = 0; k < 4; ++k) fprintf(stderr, " %7lld", h[sidx * 8 + k] ? h[sidx * 8 + k] - t0 : -1);
         fprintf(stderr, " | M");
-        for (int k = 0; k < 6; ++k) fprintf(stderr, " %7lld", h[24 * 8 + sidx * 8 + k] ? h[24 * 8 + sidx * 8 + k] - t0 : -1);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", h[24 * 8 + sidx * 8 + k] ? h[24 * 8 + sidx * 8 + k] - t0 : -1);
         fprintf(stderr, "\n");
       }
     }
