@@ -112,8 +112,7 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
-    if reserve > 0:
-        ops.set_sm_limit(torch.cuda.get_device_properties(local).multi_processor_count - reserve)
+    # (the reservation is applied by the model during backward only: model.clipmodel.nccl_sm_reserve below)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, T, Lt = args.batch, T_FRAMES, L_TOK
@@ -128,6 +127,7 @@ def run_ours(args):
     params = [p for p in model.parameters()]
     if world > 1:   # DP gradient averaging overlapped with backward (logit_scale's gradient is identical on all ranks)
         model.clipmodel.grad_ready_hook = xdist.OverlappedGradAverager()
+        model.clipmodel.nccl_sm_reserve = reserve
 
     # synthetic inputs: pinned host copies for the e2e leg, device copies for the resident leg
     g = torch.Generator().manual_seed(1234 + rank)
@@ -216,6 +216,9 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): CUDA events around every launch of one step
     roof = None
+    # per-launch / per-block CUDA-event timings below are taken with the text tower and the bias column sums on the MAIN stream:
+    # kernels that overlap on side streams would be charged each other's time
+    model.clipmodel.overlap_text_tower = model.clipmodel.overlap_colsum = False
     if rank == 0 or world > 1:
         rec = []
         ops.set_gemm_timer(rec)
@@ -255,6 +258,7 @@ def run_ours(args):
                          "fwd_bwd_tflops": round(3 * blk_flops / (f_avg + b_avg) / 1e9, 1),
                          "fwd_bwd_frac_of_peak": round(3 * blk_flops / (f_avg + b_avg) / 1e9 / pk, 4), "peak_tflops": pk}
 
+    model.clipmodel.overlap_text_tower = model.clipmodel.overlap_colsum = True
     # ---- extra (not part of `value`): the fused clip + AdamW step on this model's gradients;
     #      HBM-bound: 28 B per parameter (read p, g, m, v; write p, m, v) + 4 B for the norm pass
     opt_info = None

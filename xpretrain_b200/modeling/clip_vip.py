@@ -680,11 +680,14 @@ class _ClipVipFunction(torch.autograd.Function):
         else:
             # The text tower (~300 launches of microsecond kernels) runs on a side stream under the vision
             # tower: its small grids fill the SMs that the persistent vision kernels leave idle in their last wave.
+            # Issue order: vision first.  After a host sync (a driver reading loss.item() every step) the GPU would otherwise sit on
+            # microsecond text kernels while the host is still enqueueing them; queued behind ~600 vision launches they still
+            # start while the vision tower is executing.
             main = torch.cuda.current_stream()
             side.wait_stream(main)
+            vis = run_tower("vis")
             with torch.cuda.stream(side):
                 txt = run_tower("txt")
-            vis = run_tower("vis")
             main.wait_stream(side)
             txt.record_stream(main)
         return vis, txt
@@ -701,12 +704,18 @@ class _ClipVipFunction(torch.autograd.Function):
                 ("text_model", ctx.txt, d_txt, "text_projection.weight", _text_bwd, C_t))
         main = torch.cuda.current_stream()
         side = ctx.side if (ctx.vis is not None and ctx.txt is not None and d_vis is not None and d_txt is not None) else None
-        for tower, sv, dfeat, proj_name, bwd, C_ in reversed(jobs) if side is not None else jobs:
+        # data-parallel runs: leave `model.nccl_sm_reserve` SMs to the NCCL kernels of the overlapped gradient all-reduce for
+        # the duration of the backward pass only (the forward has no collective in flight and keeps every SM)
+        reserve = int(getattr(model, "nccl_sm_reserve", 0) or 0)
+        if reserve > 0:
+            ops.set_sm_limit(torch.cuda.get_device_properties(dev).multi_processor_count - reserve)
+        if side is not None:
+            side.wait_stream(main)            # before any vision-backward launch: the text backward only needs d_txt
+        for tower, sv, dfeat, proj_name, bwd, C_ in jobs:
             if sv is None or dfeat is None:
                 continue
             on_side = side is not None and tower == "text_model"
-            if on_side:        # text backward first in issue order, on the side stream, under the vision backward
-                side.wait_stream(main)
+            if on_side:        # text backward on the side stream, under the vision backward (issued after it, see forward)
                 dfeat.record_stream(side)
                 with torch.cuda.stream(side):
                     _tower_backward(model, ctx, tower, sv, dfeat, proj_name, bwd, C_, grads, names, named, dev)
@@ -720,6 +729,8 @@ class _ClipVipFunction(torch.autograd.Function):
         hook = getattr(model, "grad_ready_hook", None)
         if hook is not None and hasattr(hook, "finish"):
             hook.finish()      # stream-ordered wait: autograd's accumulation below sees the averaged values
+        if reserve > 0:
+            ops.set_sm_limit(0)
         ctx.vis = ctx.txt = None
         return (None, None, None, None, None, None) + tuple(grads.get(n) if r else None
                                                              for n, r in zip(names, ctx.needs_input_grad[6:]))
