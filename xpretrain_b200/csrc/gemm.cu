@@ -11,6 +11,7 @@
 #include "../../include/xpretrain_b200.h"
 #include "common.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace xp {
 
@@ -34,6 +35,7 @@ struct GemmDev {
   float alpha, col_scale;
   int wide;                 // C / aux / residual rows are 32-byte aligned (ld % 16 == 0)
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes): 64-element atom stride, 8-k-row group stride
+  int dbg;                  // profiling only (XP_GEMM_DEBUG): bit 0 = the epilogue computes but does not store
 };
 
 template <int BN>
@@ -462,6 +464,8 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
     dev.wide = (g->out != XP_OUT_BF16 || ok32(g->c, g->ldc)) && ok32(g->aux, g->ld_aux) && ok32(g->residual, g->ldr) &&
                (g->c_group_stride % 16 == 0) && (g->r_group_stride % 16 == 0);
   }
+  static const int gemm_dbg = [] { const char* e = getenv("XP_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  dev.dbg = gemm_dbg;
   dev.mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : BK * 128;
   dev.mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024;
 
