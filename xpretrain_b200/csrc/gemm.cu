@@ -36,6 +36,7 @@ struct GemmDev {
   int wide;                 // C / aux / residual rows are 32-byte aligned (ld % 16 == 0)
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes): 64-element atom stride, 8-k-row group stride
   int dbg;                  // profiling only (XP_GEMM_DEBUG): bit 0 = the epilogue computes but does not store
+  int tma_c, tma_aux;       // pair kernel: C / the aux output leave through shared-memory staging + TMA stores
 };
 
 template <int BN>
@@ -252,6 +253,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      constexpr bool kTmaEpi = false;                    // TMA-store epilogue: 2-CTA kernel only (names below are unused here)
+      const uint32_t stg = 0;
+      const CUtensorMap& tmC = tmA;
+      const CUtensorMap& tmX = tmA;
+      const int m_tile0 = 0;
+      uint32_t st_pairs = 0;
+      (void)stg; (void)tmC; (void)tmX; (void)m_tile0; (void)st_pairs;
 #include "gemm_epilogue.inc"
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -320,6 +328,9 @@ static int dispatch_out(const XpGemm* g, const CUtensorMap& tmA, const CUtensorM
 
 #include "gemm_pair.inc"
 
+// tensor maps of the TMA-store epilogue (set by xp_gemm before dispatch_pair; copies of tmA when unused)
+static thread_local CUtensorMap t_tmC, t_tmX;
+
 template <int A_MN, int B_MN, int OUT, int ACT>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& dev, int clusters,
                        cudaStream_t stream) {
@@ -341,7 +352,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  XP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, dev));
+  XP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, t_tmC, t_tmX, dev));
   XP_CHECK_LAUNCH("gemm_pair_kernel");
   return 0;
 }
@@ -469,6 +480,19 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
   dev.mn_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : BK * 128;
   dev.mn_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024;
 
+  dev.tma_c = dev.tma_aux = 0;
+  t_tmC = tmA;
+  t_tmX = tmA;
+  static const bool tma_epi_off = getenv("XP_GEMM_NO_TMA_STORE") != nullptr;
+  if (pair && g->out == XP_OUT_BF16 && g->c_group == 0 && !tma_epi_off) {
+    // epilogue through shared memory + TMA stores: boxes of 64 columns x 32 rows (one epilogue warp's rows), 128B swizzle
+    if (make_tmap_bf16_2d(&t_tmC, g->c, g->N, g->M, g->ldc, 64, 32)) return -1;
+    dev.tma_c = 1;
+    if (g->aux && (g->act == XP_ACT_QUICK_GELU || g->act == XP_ACT_GELU_ERF)) {
+      if (make_tmap_bf16_2d(&t_tmX, g->aux, g->N, g->M, g->ld_aux, 64, 32)) return -1;
+      dev.tma_aux = 1;
+    }
+  }
   if (pair) return dispatch_pair(g, tmA, tmB, dev, grid, stream);
   return bn == 256 ? dispatch_out<256>(g, tmA, tmB, dev, grid, stream)
                    : dispatch_out<128>(g, tmA, tmB, dev, grid, stream);
