@@ -488,7 +488,8 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
     // epilogue through shared memory + TMA stores: boxes of 64 columns x 32 rows (one epilogue warp's rows), 128B swizzle
     if (make_tmap_bf16_2d(&t_tmC, g->c, g->N, g->M, g->ldc, 64, 32)) return -1;
     dev.tma_c = 1;
-    if (g->aux && (g->act == XP_ACT_QUICK_GELU || g->act == XP_ACT_GELU_ERF)) {
+    static const bool tma_aux_off = getenv("XP_GEMM_NO_TMA_AUX") != nullptr;
+    if (g->aux && (g->act == XP_ACT_QUICK_GELU || g->act == XP_ACT_GELU_ERF) && !tma_aux_off) {
       if (make_tmap_bf16_2d(&t_tmX, g->aux, g->N, g->M, g->ld_aux, 64, 32)) return -1;
       dev.tma_aux = 1;
     }
