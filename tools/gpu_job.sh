@@ -1,5 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 O=gpurun_out
-run() { name=$1; shift; timeout "$TMO" "$@" > $O/$name.log 2>&1; echo "$name rc=$?"; tail -1 $O/$name.log | cut -c1-700; }
-XP_GEMM_NO_TMA_AUX=1 TMO=300 run r02k_gemm_bench_aux_direct python tools/gemm_bench.py
+run() { name=$1; shift; timeout "$TMO" "$@" > $O/$name.log 2>&1; echo "$name rc=$?"; tail -1 $O/$name.log | cut -c1-600; }
+TMO=600 run r02l_bench_timesformer python bench.py --workload timesformer --steps 8 --warmup 3
+TMO=900 run r02l_bench_swin3d python bench.py --workload swin3d --steps 5 --warmup 3
+TMO=600 run r02l_bench_ref_timesformer python bench.py --impl reference --workload timesformer --steps 3 --warmup 1
+TMO=1500 run r02l_memcheck compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_kernels.py -q -x -k "fused_gather or layernorm_with or uint8 or (vip_attention and 2-1-4-20-2) or (vip_attention and 2-2-2-100-3) or nce_loss_and_grads or gemm"
+TMO=900 run r02l_bench python bench.py --steps 8 --warmup 3
