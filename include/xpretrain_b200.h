@@ -90,10 +90,11 @@ int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, const XpRowMa
                      const float* beta, float* mean, float* rstd, int64_t rows, int32_t C, float eps, void* stream);
 /* LayerNorm fused with the residual add of the block it opens (CLIPEncoderLayer, CLIP_ViP.py:445-460: `hidden = residual +
  * branch; hidden = layer_normN(hidden)`), with the residual stream kept in fp32 as under the reference's autocast:
- *   s = x (+ add_bf16);  sum_out = s (fp32, optional);  y = LayerNorm(s).
- * x is bf16 or fp32 (x_dtype), y bf16 or fp32 (y_dtype); add / sum_out / their maps may be NULL (plain LayerNorm). */
+ *   s = x (+ add_bf16);  sum_out = s (optional);  y = LayerNorm(s).
+ * x is bf16, fp32 or fp16 (x_dtype) and so is y (y_dtype); sum_out is fp32, or fp16 when x is fp16 (saturating; the
+ * reference's own training precision under apex O2, run_pretrain.py:234-236).  add / sum_out / their maps may be NULL. */
 int xp_layernorm_add_fwd(const void* x, const XpRowMap* xmap, int32_t x_dtype, const void* add_bf16, const XpRowMap* addmap,
-                         float* sum_out, const XpRowMap* summap, void* y, const XpRowMap* ymap, int32_t y_dtype,
+                         void* sum_out, const XpRowMap* summap, void* y, const XpRowMap* ymap, int32_t y_dtype,
                          const float* gamma, const float* beta, float* mean, float* rstd, int64_t rows, int32_t C, float eps,
                          void* stream);
 /* LayerNorm backward; dx = LN'(dy) + dres (the residual-branch gradient, may be NULL);

@@ -233,6 +233,38 @@ def test_layernorm_with_fp32_residual_add_and_bias_colsum(dev, C, x_f32):
     assert rel(db, dy.float().sum(0)) < 1e-5 and rel(dg, (dy.float() * ((want_s - want_s.mean(-1, keepdim=True)) * rstd[:, None])).sum(0)) < 1e-4
 
 
+def test_layernorm_with_fp16_residual_stream(dev):
+    """`residual_dtype="fp16"` (the reference's own training precision under apex O2): x fp16 + bf16 branch -> fp32 sum inside the
+    kernel, stored as saturating fp16; the normalisation uses exactly the stored values; backward reads the fp16 input."""
+    from xpretrain_b200 import ops
+    rows, C, eps = 333, 768, 1e-5
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(rows, C, generator=g) * 3).to(dev).half()
+    x[0, 0] = 65000.0                                                               # x + add would overflow fp16: must saturate
+    add = torch.randn(rows, C, generator=g).to(dev).to(bf16)
+    add[0, 0] = 2000.0
+    gamma, beta = (1 + 0.1 * torch.randn(C, generator=g)).to(dev), (0.1 * torch.randn(C, generator=g)).to(dev)
+    y = torch.empty(rows, C, dtype=bf16, device=dev)
+    s_out = torch.empty(rows, C, dtype=torch.float16, device=dev)
+    mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    m = ops.rowmap(C)
+    ops.layernorm_fwd(x, m, y, m, gamma, beta, mean, rstd, rows, C, eps, add=add, addmap=m, sum_out=s_out, summap=m)
+    want_s = (x.float() + add.float()).clamp(-65504, 65504).half()
+    assert torch.equal(s_out, want_s) and float(s_out[0, 0]) == 65504.0
+    sr = want_s.float().requires_grad_(True)
+    want_y = F.layer_norm(sr, (C,), gamma, beta, eps)
+    assert rel(y[1:], want_y.detach()[1:]) < 4e-3
+    dy = torch.randn(rows, C, generator=g).to(dev).to(bf16)
+    want_y.backward(dy.float())
+    dx = torch.empty(rows, C, dtype=bf16, device=dev)
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    ops.layernorm_bwd(dy, m, s_out, m, gamma, mean, rstd, None, None, dx, m, dg, db, rows, C)
+    assert rel(dx[1:], sr.grad[1:]) < 4e-3
+    yh = torch.empty(rows, C, dtype=torch.float16, device=dev)                      # fp16 output (pre_layrnorm -> stream)
+    ops.layernorm_fwd(y, m, yh, m, gamma, beta, None, None, rows, C, eps)
+    assert rel(yh, F.layer_norm(y.float(), (C,), gamma, beta, eps)) < 1e-3
+
+
 def test_patchify_and_embed_tables(dev):
     from oracle import clipvip_oracle as O
     from xpretrain_b200 import ops

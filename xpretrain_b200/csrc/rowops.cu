@@ -7,6 +7,7 @@
 #include "../../include/xpretrain_b200.h"
 #include "common.h"
 #include "ptx.cuh"
+#include <cuda_fp16.h>
 
 namespace xp {
 
@@ -49,9 +50,29 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Optionally fused with the residual add in fp32 (the reference keeps the residual stream in fp32 under autocast; a bf16
 // stream costs ~2.4x its feature error, profiles/r02_parity_calibration.md):  s = x (+ add);  sum_out = s (fp32);
 // y = LN(s).  x is bf16 or fp32 (XF32), y bf16 or fp32 (YF32), add is the bf16 branch output (ADD).
-template <bool F32>
+__device__ __forceinline__ void unpack8_h(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __half22float2(h[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8_h(const float (&f)[8]) {   // saturating: a value beyond fp16's range becomes +-65504, not inf
+  uint4 u;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(f[2 * i + 1]), "f"(f[2 * i]));
+  return u;
+}
+// DT: 0 = bf16, 1 = fp32, 2 = fp16 (the residual stream may be kept in fp32, or in fp16 as under the reference's apex O2)
+template <int DT>
 __device__ __forceinline__ void ld8(const void* base, long long off, float (&f)[8]) {
-  if (F32) {
+  if (DT == 2) {
+    unpack8_h(*reinterpret_cast<const uint4*>(static_cast<const __half*>(base) + off), f);
+  } else if (DT == 1) {
     const float* p = static_cast<const float*>(base) + off;
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -59,9 +80,11 @@ __device__ __forceinline__ void ld8(const void* base, long long off, float (&f)[
     unpack8(*reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + off), f);
   }
 }
-template <bool F32>
+template <int DT>
 __device__ __forceinline__ void st8(void* base, long long off, const float (&f)[8]) {
-  if (F32) {
+  if (DT == 2) {
+    *reinterpret_cast<uint4*>(static_cast<__half*>(base) + off) = pack8_h(f);
+  } else if (DT == 1) {
     float* p = static_cast<float*>(base) + off;
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -70,10 +93,10 @@ __device__ __forceinline__ void st8(void* base, long long off, const float (&f)[
   }
 }
 
-template <bool XF32, bool YF32, bool ADD>
+template <int XT, int YT, bool ADD>
 __global__ void __launch_bounds__(128)
 ln_fwd_kernel(const void* __restrict__ x, RowMapDev xm, const __nv_bfloat16* __restrict__ add, RowMapDev am,
-              float* __restrict__ sum_out, RowMapDev sm, void* __restrict__ y, RowMapDev ym,
+              void* __restrict__ sum_out, RowMapDev sm, void* __restrict__ y, RowMapDev ym,
               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean_out,
               float* __restrict__ rstd_out, long long rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
@@ -89,13 +112,19 @@ ln_fwd_kernel(const void* __restrict__ x, RowMapDev xm, const __nv_bfloat16* __r
   for (int i = 0; i < LN_MAX_VEC; ++i) {
     const int c = lane + i * 32;
     if (c < nvec) {
-      ld8<XF32>(x, xo + c * 8, v[i]);
+      ld8<XT>(x, xo + c * 8, v[i]);
       if (ADD) {
         float a[8];
         unpack8(*reinterpret_cast<const uint4*>(add + ao + c * 8), a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] += a[j];
-        if (sum_out) st8<true>(sum_out, so + c * 8, v[i]);
+        if (XT == 2) {                       // fp16 stream: normalise exactly the rounded values that are stored / read back later
+          const uint4 hv = pack8_h(v[i]);
+          unpack8_h(hv, v[i]);
+          if (sum_out) *reinterpret_cast<uint4*>(static_cast<__half*>(sum_out) + so + c * 8) = hv;
+        } else if (sum_out) {                // bf16 / fp32 x: the stream is stored in fp32
+          st8<1>(sum_out, so + c * 8, v[i]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
@@ -126,7 +155,7 @@ ln_fwd_kernel(const void* __restrict__ x, RowMapDev xm, const __nv_bfloat16* __r
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
-      st8<YF32>(y, yo + c * 8, o);
+      st8<YT>(y, yo + c * 8, o);
     }
   }
   if (lane == 0) {
@@ -142,7 +171,7 @@ constexpr int LNB_WARPS = 8;
 // RSUM: additionally accumulate the column sums of dres into dres_sum — dres is the gradient of a residual add whose other
 // branch ends in a Linear, so its column sum IS that Linear's bias gradient (fc2.bias from LN2's dres, out_proj.bias from
 // LN1's): the pass that already streams dres produces it, and the standalone colsum launches disappear.
-template <int NVEC, bool RSUM, bool XF32>
+template <int NVEC, bool RSUM, int XT>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 2)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const void* __restrict__ x, RowMapDev xm,
               const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -169,12 +198,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const void* _
     const __nv_bfloat16* dyr = dy + row_addr(dym, r);
     const __nv_bfloat16* drr = dres ? dres + row_addr(drm, r) : nullptr;
     const float mu = mean[r], rs = rstd[r];
+    constexpr bool XF32 = XT == 1;
     uint4 xraw[XF32 ? 1 : NVEC], draw[NVEC], rraw[NVEC];     // an fp32 x is re-read (L1) in the second pass, not kept
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        if (!XF32) xraw[i] = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x) + xo + c * 8);
+        if (!XF32) xraw[i] = *reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(x) + xo + c * 8);
         draw[i] = *reinterpret_cast<const uint4*>(dyr + c * 8);
         if (drr) rraw[i] = *reinterpret_cast<const uint4*>(drr + c * 8);
       }
@@ -185,7 +215,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const void* _
       const int c = lane + i * 32;
       if (c < nvec) {
         float xv[8], dv[8];
-        if (XF32) ld8<true>(x, xo + c * 8, xv);
+        if (XF32) ld8<1>(x, xo + c * 8, xv);
+        else if (XT == 2) unpack8_h(xraw[i], xv);
         else unpack8(xraw[i], xv);
         unpack8(draw[i], dv);
 #pragma unroll
@@ -207,7 +238,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowMapDev dym, const void* _
       const int c = lane + i * 32;
       if (c < nvec) {
         float xv[8], dv[8], o[8];
-        if (XF32) ld8<true>(x, xo + c * 8, xv);
+        if (XF32) ld8<1>(x, xo + c * 8, xv);
+        else if (XT == 2) unpack8_h(xraw[i], xv);
         else unpack8(xraw[i], xv);
         unpack8(draw[i], dv);
 #pragma unroll
@@ -571,13 +603,14 @@ extern "C" int xp_layernorm_fwd(const void* x, const XpRowMap* xmap, void* y, co
 }
 
 extern "C" int xp_layernorm_add_fwd(const void* x, const XpRowMap* xmap, int32_t x_dtype, const void* add_bf16,
-                                    const XpRowMap* addmap, float* sum_out, const XpRowMap* summap, void* y,
+                                    const XpRowMap* addmap, void* sum_out, const XpRowMap* summap, void* y,
                                     const XpRowMap* ymap, int32_t y_dtype, const float* gamma, const float* beta, float* mean,
                                     float* rstd, int64_t rows, int32_t C, float eps, void* stream) {
   XP_ENTER(x);
   if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_fwd: C must be a multiple of 8 and <= 1024");
-  if ((x_dtype != XP_DTYPE_BF16 && x_dtype != XP_DTYPE_F32) || (y_dtype != XP_DTYPE_BF16 && y_dtype != XP_DTYPE_F32))
-    return fail("xp_layernorm_add_fwd: x / y dtype must be XP_DTYPE_BF16 or XP_DTYPE_F32");
+  if ((x_dtype != XP_DTYPE_BF16 && x_dtype != XP_DTYPE_F32 && x_dtype != XP_DTYPE_F16) ||
+      (y_dtype != XP_DTYPE_BF16 && y_dtype != XP_DTYPE_F32 && y_dtype != XP_DTYPE_F16))
+    return fail("xp_layernorm_add_fwd: x / y dtype must be XP_DTYPE_BF16, XP_DTYPE_F32 or XP_DTYPE_F16");
   if (add_bf16 != nullptr && addmap == nullptr) return fail("xp_layernorm_add_fwd: add needs its row map");
   if (sum_out != nullptr && (add_bf16 == nullptr || summap == nullptr)) return fail("xp_layernorm_add_fwd: sum_out needs add and its row map");
   if (rows <= 0) return 0;
@@ -586,17 +619,25 @@ extern "C" int xp_layernorm_add_fwd(const void* x, const XpRowMap* xmap, int32_t
   XpRowMap none = {0, 0, 0, nullptr};
   const RowMapDev xm = to_dev(*xmap), am = to_dev(addmap ? *addmap : none), sm = to_dev(summap ? *summap : none), ym = to_dev(*ymap);
   const __nv_bfloat16* add = static_cast<const __nv_bfloat16*>(add_bf16);
-#define XP_LNF(XF, YF, AD) \
-  ln_fwd_kernel<XF, YF, AD><<<grid, 128, 0, st>>>(x, xm, add, am, sum_out, sm, y, ym, gamma, beta, mean, rstd, rows, C, eps)
-  const bool xf = x_dtype == XP_DTYPE_F32, yf = y_dtype == XP_DTYPE_F32, ad = add_bf16 != nullptr;
-  if (!xf && !yf && !ad) XP_LNF(false, false, false);
-  else if (!xf && !yf && ad) XP_LNF(false, false, true);
-  else if (!xf && yf && !ad) XP_LNF(false, true, false);
-  else if (!xf && yf && ad) XP_LNF(false, true, true);
-  else if (xf && !yf && !ad) XP_LNF(true, false, false);
-  else if (xf && !yf && ad) XP_LNF(true, false, true);
-  else if (xf && yf && !ad) XP_LNF(true, true, false);
-  else XP_LNF(true, true, true);
+#define XP_LNF(XT_, YT_, AD) \
+  ln_fwd_kernel<XT_, YT_, AD><<<grid, 128, 0, st>>>(x, xm, add, am, sum_out, sm, y, ym, gamma, beta, mean, rstd, rows, C, eps)
+  // dtype codes of the kernels: 0 bf16, 1 fp32, 2 fp16
+  const int xt = x_dtype == XP_DTYPE_F32 ? 1 : (x_dtype == XP_DTYPE_F16 ? 2 : 0);
+  const int yt = y_dtype == XP_DTYPE_F32 ? 1 : (y_dtype == XP_DTYPE_F16 ? 2 : 0);
+  const bool ad = add_bf16 != nullptr;
+#define XP_LNF_Y(XT_)                                      \
+  do {                                                     \
+    if (yt == 0 && !ad) XP_LNF(XT_, 0, false);             \
+    else if (yt == 0 && ad) XP_LNF(XT_, 0, true);          \
+    else if (yt == 1 && !ad) XP_LNF(XT_, 1, false);        \
+    else if (yt == 1 && ad) XP_LNF(XT_, 1, true);          \
+    else if (yt == 2 && !ad) XP_LNF(XT_, 2, false);        \
+    else XP_LNF(XT_, 2, true);                             \
+  } while (0)
+  if (xt == 0) XP_LNF_Y(0);
+  else if (xt == 1) XP_LNF_Y(1);
+  else XP_LNF_Y(2);
+#undef XP_LNF_Y
 #undef XP_LNF
   XP_CHECK_LAUNCH("ln_fwd_kernel");
   return 0;
@@ -607,7 +648,8 @@ extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const voi
                                 const XpRowMap* drmap, void* dx, const XpRowMap* dxmap, float* dgamma, float* dbeta,
                                 float* dres_colsum, int64_t rows, int32_t C, void* stream) {
   XP_ENTER(dy);
-  if (x_dtype != XP_DTYPE_BF16 && x_dtype != XP_DTYPE_F32) return fail("xp_layernorm_bwd: x dtype must be XP_DTYPE_BF16 or XP_DTYPE_F32");
+  if (x_dtype != XP_DTYPE_BF16 && x_dtype != XP_DTYPE_F32 && x_dtype != XP_DTYPE_F16)
+    return fail("xp_layernorm_bwd: x dtype must be XP_DTYPE_BF16, XP_DTYPE_F32 or XP_DTYPE_F16");
   if (C % 8 || C > LN_MAX_VEC * 256) return fail("xp_layernorm_bwd: C must be a multiple of 8 and <= 1024");
   if (dres_colsum != nullptr && dres == nullptr) return fail("xp_layernorm_bwd: dres_colsum needs dres");
   if (rows <= 0) return 0;
@@ -617,7 +659,7 @@ extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const voi
   const size_t smem = (static_cast<size_t>(LNB_WARPS) * (rsum ? 3 : 2) + 1) * C * sizeof(float);
   XpRowMap none = {0, 0, 0, nullptr};
   const int nv = (C / 8 + 31) / 32;
-  const bool xf32 = x_dtype == XP_DTYPE_F32;
+  const int xt = x_dtype == XP_DTYPE_F32 ? 1 : (x_dtype == XP_DTYPE_F16 ? 2 : 0);
 #define XP_LNB_LAUNCH(NV, RS, XF)                                                                                   \
   do {                                                                                                              \
     static bool attr = false;                                                                                       \
@@ -631,12 +673,14 @@ extern "C" int xp_layernorm_bwd(const void* dy, const XpRowMap* dymap, const voi
         gamma, mean, rstd, static_cast<const __nv_bfloat16*>(dres), to_dev(drmap ? *drmap : none),                  \
         static_cast<__nv_bfloat16*>(dx), to_dev(*dxmap), dgamma, dbeta, dres_colsum, rows, C);                      \
   } while (0)
-#define XP_LNB_PICK(NV)                                \
-  do {                                                 \
-    if (rsum && xf32) XP_LNB_LAUNCH(NV, true, true);   \
-    else if (rsum) XP_LNB_LAUNCH(NV, true, false);     \
-    else if (xf32) XP_LNB_LAUNCH(NV, false, true);     \
-    else XP_LNB_LAUNCH(NV, false, false);              \
+#define XP_LNB_PICK(NV)                                    \
+  do {                                                     \
+    if (rsum && xt == 1) XP_LNB_LAUNCH(NV, true, 1);       \
+    else if (rsum && xt == 2) XP_LNB_LAUNCH(NV, true, 2);  \
+    else if (rsum) XP_LNB_LAUNCH(NV, true, 0);             \
+    else if (xt == 1) XP_LNB_LAUNCH(NV, false, 1);         \
+    else if (xt == 2) XP_LNB_LAUNCH(NV, false, 2);         \
+    else XP_LNB_LAUNCH(NV, false, 0);                      \
   } while (0)
   if (nv == 1) XP_LNB_PICK(1);
   else if (nv == 2) XP_LNB_PICK(2);

@@ -49,7 +49,8 @@ class ClipVipConfig:
     vocab_size: int = 49408
     max_position_embeddings: int = 77
     layer_norm_eps: float = 1e-5
-    residual_fp32: bool = True          # keep the residual stream in fp32 (as the reference does under bf16 autocast)
+    residual_fp32: bool = True          # keep the residual stream out of bf16 (as the reference does under bf16 autocast)
+    residual_dtype: str = "fp32"        # its storage type: "fp32", or "fp16" (apex-O2-like: bf16's HBM cost, 8x finer rounding)
     temporal_size: int = 12
     if_use_temporal_embed: int = 1
     add_cls_num: int = 3
@@ -261,16 +262,27 @@ def _small_bf16(model: CLIPModel, name: str, p: torch.Tensor) -> torch.Tensor:
 
 # --------------------------------------------------------------------------- encoder layers
 def _residual_fp32(model) -> bool:
-    """The residual stream is kept in fp32 (as under the reference's bf16 autocast, where only the Linear / matmul inputs are
+    """The residual stream is kept OUT of bf16 (as under the reference's bf16 autocast, where only the Linear / matmul inputs are
     rounded): the block outputs stay bf16 branch tensors and the add happens in fp32 inside the next LayerNorm kernel.
     `model.config.residual_fp32 = False` (or XP_RESIDUAL_BF16=1) selects the round-1 path: bf16 stream, add in the GEMM epilogue."""
     import os
     return bool(getattr(model.config, "residual_fp32", True)) and os.environ.get("XP_RESIDUAL_BF16") != "1"
 
 
-def _layer_fwd(x, pend, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, rows: int, save: bool, fp32res: bool):
-    """One pre-LN residual block (CLIP_ViP.py:445-460).  x: residual stream [rows, C] (bf16, or fp32 with `fp32res`); pend: the
-    previous block's bf16 branch output that still has to be added to it (fp32res only).  Returns (x_out, pend_out, saved)."""
+def _stream_dtype(model) -> torch.dtype:
+    """Storage type of the residual stream between the fused add + LayerNorm kernels: fp32 (default), or fp16
+    (`config.residual_dtype = "fp16"` / XP_RESIDUAL_DTYPE=fp16): 11 mantissa bits instead of bf16's 8 at bf16's HBM cost — the
+    precision the reference itself trains in under apex O2 (run_pretrain.py:234-236); values saturate at +-65504."""
+    import os
+    name = os.environ.get("XP_RESIDUAL_DTYPE") or getattr(model.config, "residual_dtype", "fp32")
+    return torch.float16 if str(name) in ("fp16", "float16", "half") else f32
+
+
+def _layer_fwd(x, pend, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, rows: int, save: bool, stream_dt):
+    """One pre-LN residual block (CLIP_ViP.py:445-460).  x: residual stream [rows, C] in `stream_dt` (fp32 / fp16), or bf16 when
+    stream_dt is None (round-1 path); pend: the previous block's bf16 branch output that still has to be added to it.
+    Returns (x_out, pend_out, saved)."""
+    fp32res = stream_dt is not None
     C_, I = pk.C, pk.I
     dev = x.device
     plain = ops.rowmap(C_)
@@ -278,7 +290,7 @@ def _layer_fwd(x, pend, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, ro
     h = torch.empty(rows, C_, dtype=bf16, device=dev)
     ln1, ln2 = layer.layer_norm1, layer.layer_norm2
     if pend is not None:        # x <- x + pend in fp32, fused into layer_norm1
-        xs = torch.empty(rows, C_, dtype=f32, device=dev)
+        xs = torch.empty(rows, C_, dtype=stream_dt, device=dev)
         ops.layernorm_fwd(x, plain, h, plain, ln1.weight, ln1.bias, mean1, rstd1, rows, C_, eps, add=pend, addmap=plain,
                           sum_out=xs, summap=plain)
         x = xs
@@ -294,7 +306,7 @@ def _layer_fwd(x, pend, layer, pk: _WeightPack, i: int, eps: float, attn_fwd, ro
     if fp32res:
         y1 = torch.empty(rows, C_, dtype=bf16, device=dev)
         ops.linear_fwd(a, pk.wo[i], layer.self_attn.out_proj.bias, y1)                  # branch only: the add is in layer_norm2
-        x1 = torch.empty(rows, C_, dtype=f32, device=dev)
+        x1 = torch.empty(rows, C_, dtype=stream_dt, device=dev)
         ops.layernorm_fwd(x, plain, h2, plain, ln2.weight, ln2.bias, mean2, rstd2, rows, C_, eps, add=y1, addmap=plain,
                           sum_out=x1, summap=plain)
         del y1
@@ -324,7 +336,7 @@ def _pooled_ln(x, pend, rmap, ln, B: int, C_: int, eps: float):
     if pend is None:
         ops.layernorm_fwd(x, rmap, pooled, plain, ln.weight, ln.bias, mean, rstd, B, C_, eps)
         return pooled, mean, rstd, (x, rmap)
-    rows_in = torch.empty(B, C_, dtype=f32, device=dev)
+    rows_in = torch.empty(B, C_, dtype=torch.float16 if x.dtype == torch.float16 else f32, device=dev)
     ops.layernorm_fwd(x, rmap, pooled, plain, ln.weight, ln.bias, mean, rstd, B, C_, eps, add=pend, addmap=rmap, sum_out=rows_in,
                       summap=plain)
     return pooled, mean, rstd, (rows_in, plain)
@@ -464,8 +476,8 @@ def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
     gmap = ops.rowmap(C_, group=M, group_stride=S * C_)
     mean0p = torch.empty(B * T * L, dtype=f32, device=dev); rstd0p = torch.empty_like(mean0p)
     mean0g = torch.empty(B * M, dtype=f32, device=dev); rstd0g = torch.empty_like(mean0g)
-    fp32res = _residual_fp32(model)
-    x = torch.empty(rows, C_, dtype=f32 if fp32res else bf16, device=dev)
+    stream_dt = _stream_dtype(model) if _residual_fp32(model) else None
+    x = torch.empty(rows, C_, dtype=stream_dt if stream_dt is not None else bf16, device=dev)
     ln0 = vm.pre_layrnorm
     ops.layernorm_fwd(x0, pmap, x, pmap, ln0.weight, ln0.bias, mean0p, rstd0p, B * T * L, C_, eps, x_off=M * C_,
                       y_off=M * C_)
@@ -485,7 +497,7 @@ def _vision_fwd(model: CLIPModel, video: torch.Tensor, save: bool):
         if timer is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        x, pend, sv = _layer_fwd(x, pend, layer, pk, i, eps, attn_fwd, rows, save, fp32res)
+        x, pend, sv = _layer_fwd(x, pend, layer, pk, i, eps, attn_fwd, rows, save, stream_dt)
         if timer is not None:
             e1.record()
             timer.append(("fwd", e0, e1))
@@ -588,9 +600,11 @@ def _text_fwd(model: CLIPModel, input_ids: torch.Tensor, attention_mask: Optiona
 
     layer_saved = []
     pend = None
-    fp32res = _residual_fp32(model)
+    stream_dt = _stream_dtype(model) if _residual_fp32(model) else None
+    if stream_dt is not None:
+        x = x.to(stream_dt)          # [B*Lt, 512]: the token + position embeddings enter the stream in its storage type
     for i, layer in enumerate(tm.encoder.layers):
-        x, pend, sv = _layer_fwd(x, pend, layer, pk, i, eps, attn_fwd, rows, save, fp32res)
+        x, pend, sv = _layer_fwd(x, pend, layer, pk, i, eps, attn_fwd, rows, save, stream_dt)
         layer_saved.append(sv)
     # final_layer_norm is per-row, so it is applied to the pooled EOS row only (first argmax of the ids, :776)
     eos = torch.empty(B, dtype=torch.int64, device=dev)

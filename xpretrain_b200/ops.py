@@ -142,9 +142,9 @@ def layernorm_fwd(x, xmap, y, ymap, gamma, beta, mean, rstd, rows: int, C_: int,
                   add=None, addmap=None, add_off=0, sum_out=None, summap=None):
     """y = LayerNorm(x (+ add)); offsets in ELEMENTS of the respective tensor.  x / y may be bf16 or fp32 (the fp32 residual
     stream); `add` is the bf16 branch output folded in before the normalisation, `sum_out` (fp32) receives x + add."""
-    dt = {torch.bfloat16: _lib.DTYPE_BF16, torch.float32: _lib.DTYPE_F32}
+    dt = {torch.bfloat16: _lib.DTYPE_BF16, torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
     assert add is None or add.dtype == bf16
-    assert sum_out is None or sum_out.dtype == f32
+    assert sum_out is None or sum_out.dtype == (torch.float16 if x.dtype == torch.float16 else f32)
     check(lib().xp_layernorm_add_fwd(_p(x) + x_off * x.element_size(), C.byref(xmap), dt[x.dtype],
                                      (_p(add) + add_off * 2) if add is not None else None,
                                      C.byref(addmap) if addmap is not None else None, _p(sum_out),
@@ -155,8 +155,8 @@ def layernorm_fwd(x, xmap, y, ymap, gamma, beta, mean, rstd, rows: int, C_: int,
 
 def layernorm_bwd(dy, dymap, x, xmap, gamma, mean, rstd, dres, drmap, dx, dxmap, dgamma, dbeta, rows: int, C_: int,
                   dy_off=0, x_off=0, dres_off=0, dx_off=0, dres_colsum=None):
-    """x: the saved LayerNorm input, bf16 or fp32; dy / dres / dx bf16.  Offsets in elements."""
-    dt = {torch.bfloat16: _lib.DTYPE_BF16, torch.float32: _lib.DTYPE_F32}
+    """x: the saved LayerNorm input, bf16, fp32 or fp16; dy / dres / dx bf16.  Offsets in elements."""
+    dt = {torch.bfloat16: _lib.DTYPE_BF16, torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
     check(lib().xp_layernorm_bwd(_p(dy) + dy_off * 2, C.byref(dymap), _p(x) + x_off * x.element_size(), C.byref(xmap),
                                  dt[x.dtype], _p(gamma), _p(mean), _p(rstd),
                                  (_p(dres) + dres_off * 2) if dres is not None else None,
