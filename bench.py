@@ -341,15 +341,15 @@ def run_ours(args):
 
 
 def ncu_traffic():
-    """(dram__bytes_read + dram__bytes_write of one captured GEMM launch, what that launch was) from
-    profiles/r01_ncu_gemm_traffic.json; (None, None) when no capture is committed."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_gemm_traffic.json")
+    """(dram__bytes_read + dram__bytes_write of one captured GEMM launch, what that launch was) from the committed ncu capture
+    profiles/r02_ncu_gemm_traffic.json (a property of that capture, not of this run); (None, None) when none is committed."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_gemm_traffic.json")
     try:
         with open(path) as f:
             d = json.load(f)
         return d["traffic_bytes"], {"algorithmic_bytes": d["algorithmic_bytes"]["total"],
                                     "launch": f"{d['kernel']} M={d['shape']['M']} N={d['shape']['N']} K={d['shape']['K']}",
-                                    "source": "profiles/r01_ncu_gemm_traffic.json (one ncu --set full capture)"}
+                                    "source": "profiles/r02_ncu_gemm_traffic.json (one ncu --set full capture of this kernel, not of this run)"}
     except (OSError, KeyError, ValueError):
         return None, None
 
@@ -528,8 +528,8 @@ def _encoder_oracle(kind, batch, seed):
     cfg = SO.Swin3DCfg()
     sd = SO.init_state_dict(cfg, seed=0)
     x = SO.synthetic_video(batch, 32, 224, 224, cfg, seed=seed)
-    oshape = (batch, 32, 224 // 64, 224 // 64, 1024)
-    w_out = torch.randn(oshape, generator=g) / (32 * 3 * 3 * 1024) ** 0.5
+    oshape = (batch, 32, 4, 4, 1024)          # 224 / 8 = 28 -> 14 -> 7 -> 4 (odd sizes are zero-padded by PatchMerging, :283-305)
+    w_out = torch.randn(oshape, generator=g) / (32 * 4 * 4 * 1024) ** 0.5
     return sd, x, w_out, (lambda sdo, xin: SO.swin3d_forward(sdo, xin, cfg))
 
 
