@@ -126,7 +126,8 @@ def run_ours(args):
     model = model.to(dev)
     params = [p for p in model.parameters()]
     if world > 1:   # DP gradient averaging overlapped with backward (logit_scale's gradient is identical on all ranks)
-        model.clipmodel.grad_ready_hook = xdist.OverlappedGradAverager()
+        comm = torch.bfloat16 if os.environ.get("XP_GRAD_COMM", "fp32") == "bf16" else None
+        model.clipmodel.grad_ready_hook = xdist.OverlappedGradAverager(comm_dtype=comm)
         model.clipmodel.nccl_sm_reserve = reserve
 
     # synthetic inputs: pinned host copies for the e2e leg, device copies for the resident leg
@@ -314,7 +315,7 @@ def run_ours(args):
                                f"{'/[2]' if world > 1 else ''}); step = fwd + gather + InfoNCE + bwd"
                                f"{' + DP grad all-reduce' if world > 1 else ''}",
                    "global_batch": pairs, "frames": T, "tokens": Lt, "parallelism": f"dp{world}",
-                   "sm_reserve_for_nccl": reserve,
+                   "sm_reserve_for_nccl": reserve, "grad_allreduce_dtype": os.environ.get("XP_GRAD_COMM", "fp32") if world > 1 else None,
                    "l2": "inputs (462 MB video + 40 GB activations per step) far exceed the 126 MB L2",
                    "weights": "random init with the reference's init statistics, fp32 masters, bf16 compute copies"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 3),

@@ -94,16 +94,27 @@ class OverlappedGradAverager:
     the compute stream wait for the outstanding collectives.  Equivalent to hvd.DistributedOptimizer's backward
     hooks + synchronize() (run_pretrain.py:226-228,379)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, comm_dtype=None):
+        """comm_dtype=torch.bfloat16 halves the bytes on the wire (and the time NCCL's CTAs compete with the backward GEMMs):
+        each bucket is cast to bf16, averaged, and written back into the fp32 gradient buffer.  The reference's own
+        all-reduce runs on fp16 gradients (apex O2 model gradients, run_pretrain.py:234-236); the default keeps fp32."""
         self.group = group
+        self.comm_dtype = comm_dtype
         self.pending = []
 
     def __call__(self, flat: torch.Tensor) -> None:
         if world_size(self.group) == 1:
             return
-        self.pending.append(dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        if self.comm_dtype is not None and self.comm_dtype != flat.dtype:
+            buf = flat.to(self.comm_dtype)
+            work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self.pending.append((work, buf, flat))
+        else:
+            self.pending.append((dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None, None))
 
     def finish(self) -> None:
-        for work in self.pending:
+        for work, buf, flat in self.pending:
             work.wait()
+            if buf is not None:
+                flat.copy_(buf)
         self.pending = []
