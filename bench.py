@@ -103,9 +103,10 @@ def run_ours(args):
     from xpretrain_b200.optimization.loss import gather_nce_loss
     from xpretrain_b200.utils import distributed as xdist
 
-    # N > 1: the overlapped gradient all-reduce needs ~9 GB/s of a 900 GB/s fabric — give NCCL a handful of CTAs and keep them
-    # off the SMs of the persistent GEMMs (XP_SM_RESERVE SMs are left out of every GEMM grid; 0 disables)
-    reserve = int(os.environ.get("XP_SM_RESERVE", "4")) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0
+    # N > 1, optional (XP_SM_RESERVE=n, default 0): cap NCCL at n CTAs and leave n SMs out of every backward GEMM grid so that the
+    # overlapped gradient all-reduce never displaces a persistent GEMM CTA.  Measured: +2.8 % at 2 GPUs, but -2.6 % at 8 GPUs, where
+    # the thinner all-reduce (1.75x the bytes per rank) exposes its tail (profiles/r02_bench_n8_*.json) — hence off by default.
+    reserve = int(os.environ.get("XP_SM_RESERVE", "0")) if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0
     if reserve > 0:
         os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
     rank, local, world = xdist.init_from_env("nccl")
