@@ -216,6 +216,28 @@ def run_ours(args):
     ms_e2e = float(ms_t) / args.steps
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
+    # ---- extra: the same e2e loop fed with the decoder's uint8 [B, T, H, W, 3] frames — the reference's
+    #      `/255` + Normalize runs inside the patch-extraction kernel, a step uploads 1 byte per sample value instead of 4
+    e2e_u8 = None
+    if world == 1:
+        gu = torch.Generator().manual_seed(99)
+        host_u8 = [(torch.randint(0, 256, (B, T, 224, 224, 3), dtype=torch.uint8, generator=gu).pin_memory(), h[1], h[2])
+                   for h in host]
+        host_f32, host[:] = list(host), host_u8
+        e2e_loop(2)
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        e2e_loop(args.steps)
+        u1.record()
+        barrier()
+        ms_u8 = u0.elapsed_time(u1) / args.steps
+        e2e_u8 = {"what": "module API, pinned uint8 HWC frames (preprocessing fused into the patch extraction) + loss.item() per step",
+                  "value": round(B / ms_u8 * 1e3, 2), "unit": UNIT, "ms_per_step": round(ms_u8, 3),
+                  "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_u8[0]), "d2h_bytes_per_step": 4}
+        host[:] = host_f32
+        del host_u8
+
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): CUDA events around every launch of one step
     roof = None
     # per-launch / per-block CUDA-event timings below are taken with the text tower and the bias column sums on the MAIN stream:
@@ -321,6 +343,7 @@ def run_ours(args):
                    "weights": "random init with the reference's init statistics, fp32 masters, bf16 compute copies"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": last["loss"]},
+        "e2e_uint8_frames": e2e_u8,
         "gpu_launches": int(launches * world),
         "clocks": clocks,
         "roofline": roof,
