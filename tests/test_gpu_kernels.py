@@ -377,6 +377,31 @@ def test_vip_attention_fwd_bwd(dev, B, H, T, L, M):
             assert rel(got.view(B, S, 3 * C)[:, :M, sl], qr.grad.view(B, S, 3 * C)[:, :M, sl]) < 2e-2, (impl, name, "global rows")
 
 
+def test_vip_attention_forward_rescales_when_later_keys_dominate(dev):
+    """The forward reads S once and takes exponentials relative to a running reference that moves only when a chunk of keys
+    exceeds it by e^8; then the P chunks already written are rescaled.  Keys whose logits grow along the sequence (each 16-key
+    chunk beats the previous ones by far more than 8) force that path at every chunk, for frame and for global queries."""
+    from xpretrain_b200 import ops
+    B, H, T, L, M = 1, 2, 2, 196, 4
+    C, S = 64 * H, M + T * L
+    g = torch.Generator(device="cpu").manual_seed(17)
+    qkv = torch.randn(B * S, 3 * C, generator=g) * 0.5
+    ramp = torch.cat([torch.linspace(4.0, 6.0, M), torch.linspace(0.2, 12.0, L).repeat(T)])     # per key row
+    base = torch.randn(1, C, generator=g).sign()                                              # a common direction: q.k grows with the ramp
+    qkv[:, :C] = 0.35 * (base + 0.1 * torch.randn(B * S, C, generator=g))
+    qkv[:, C:2 * C] = ramp[:, None] * (base + 0.05 * torch.randn(B * S, C, generator=g))
+    qkv = qkv.to(dev).to(bf16)
+    ref, ref_lse = _vip_ref(qkv.float(), B, H, T, L, M, C)
+    s_ref = (qkv.float()[:, :C].reshape(B, S, H, 64).transpose(1, 2) @ qkv.float()[:, C:2 * C].reshape(B, S, H, 64).transpose(1, 2).transpose(-1, -2))
+    assert float(s_ref.max() - s_ref.min()) > 100                                              # the logits really span > e^8 many times
+    out = torch.zeros(B * S, C, dtype=bf16, device=dev)
+    lse = torch.zeros(B, H, S, device=dev)
+    ws = ops.vip_attention_workspace(B, H, T, M, dev)
+    ops.vip_attention_fwd_tc(qkv, out, lse, ws, B, H, T, L, M, C)
+    assert rel(out, ref) < 8e-3
+    assert float(((lse - ref_lse).abs() / ref_lse.abs().clamp_min(1.0)).max()) < 1e-3
+
+
 @pytest.mark.parametrize("Lt", [32, 77, 5])
 def test_text_attention_fwd_bwd(dev, Lt):
     from oracle import clipvip_oracle as O
