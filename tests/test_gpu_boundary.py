@@ -104,8 +104,10 @@ def test_inplace_data_updates_of_the_reference_adamw_reach_the_next_forward(dev)
     assert _rel(out1["vis_features"], out0["vis_features"].detach()) > 5e-2                 # the forward moved ...
     new_sd = {k: v.detach().cpu() for k, v in model.clipmodel.state_dict().items()}
     want = O.clip_vip_forward(new_sd, video, ids, mask, cfg)                                 # ... to where the fp32 oracle goes
-    assert _rel(out1["vis_features"].cpu(), want["vis_features"]) < 1e-2
-    assert _rel(out1["text_features"].cpu(), want["text_features"]) < 1e-2
+    # (an lr = 2e-2 step moves every weight by about its own initial scale: activations grow and so does the bf16 error; the
+    # stale-weights failure this test guards against is a 100 % error, the bar only has to separate the two)
+    assert _rel(out1["vis_features"].cpu(), want["vis_features"]) < 2e-2
+    assert _rel(out1["text_features"].cpu(), want["text_features"]) < 2e-2
     # same contract for load_state_dict and overload_logit_scale-style fills
     model.clipmodel.load_state_dict(sd, strict=False)
     with torch.no_grad():

@@ -378,9 +378,9 @@ def test_vip_attention_fwd_bwd(dev, B, H, T, L, M):
 
 
 def test_vip_attention_forward_rescales_when_later_keys_dominate(dev):
-    """The forward reads S once and takes exponentials relative to a running reference that moves only when a chunk of keys
-    exceeds it by e^8; then the P chunks already written are rescaled.  Keys whose logits grow along the sequence (each 16-key
-    chunk beats the previous ones by far more than 8) force that path at every chunk, for frame and for global queries."""
+    """Softmax range stress: keys whose logits grow along the sequence by far more than e^8 per 16-key chunk (the row maximum
+    sits in the last chunk; a one-pass variant with a running reference — tried in round 2 and 15 % slower than the two-pass
+    kernel, profiles/r02_attn_fwd_single_pass.md — has to rescale at every chunk), for frame and for global queries."""
     from xpretrain_b200 import ops
     B, H, T, L, M = 1, 2, 2, 196, 4
     C, S = 64 * H, M + T * L

@@ -200,13 +200,8 @@ vip_attn_fwd_tc_kernel(const __grid_constant__ TfMaps tm, __nv_bfloat16* __restr
       const bool mask_gk = is_glob && (t != 0);   // a global query counts the global keys in frame 0 only
       mbar_wait(&s_ready[j], pp);
       tc_fence_after();
-      // ---- ONE pass over S.  `tcgen05.ld` delivers ~64 B/clk/SM (profiles/r02_attn_bwd_trace.md), so reading the 224-column
-      // tile twice (row maximum, then exponentials) was this kernel's largest cost.  The exponentials are taken relative to a
-      // running reference `mx` that only moves when a chunk's maximum exceeds it by more than TC_SLACK (P <= e^8 otherwise:
-      // harmless in bf16 / fp32); when it moves, the sum and the P chunks already written are rescaled (rare: the first live
-      // chunk sets the reference, later chunks seldom beat it by e^8).  Packed bf16 P overwrites S columns already consumed.
-      constexpr float TC_SLACK = 8.f;
-      float mx = -INFINITY, mb = 0.f, sum = 0.f;
+      // ---- pass 1: row maximum (software-pipelined TMEM loads; chunks with only live keys skip the masks)
+      float mx = -INFINITY;
       uint32_t r[2][16];
       if (warp_active) {
         tmem_ld16(t_lane, r[0]);
@@ -214,43 +209,44 @@ vip_attn_fwd_tc_kernel(const __grid_constant__ TfMaps tm, __nv_bfloat16* __restr
         for (int c = 0; c < (TC_FK + TC_GK) / 16; ++c) {
           tmem_ld_wait16(r[c & 1]);
           if (c + 1 < (TC_FK + TC_GK) / 16) tmem_ld16(t_lane + (c + 1) * 16, r[(c + 1) & 1]);
-          const bool all_live = c * 16 + 16 <= d.L;
-          float cm = -INFINITY;
+          if (c * 16 + 16 <= d.L) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = c * 16 + i;
-            const bool dead = !all_live && (col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk));
-            cm = fmaxf(cm, dead ? -INFINITY : __uint_as_float(r[c & 1][i]));
-          }
-          const bool move = cm > mx + TC_SLACK;          // this row moves its reference (always true at its first live chunk)
-          // tcgen05.ld / .st are warp-collective (.sync.aligned): the rescale below runs for the WHOLE warp whenever any row needs
-          // it, rows that do not get the factor 1
-          if (c > 0 && __any_sync(0xffffffffu, move && mx != -INFINITY)) {
-            const float f = (move && mx != -INFINITY) ? tc_exp2((mx - cm) * TC_LOG2E) : 1.f;
-            sum *= f;
-            tmem_st_wait();                              // our earlier P stores must be visible to the loads below
-#pragma unroll 1
-            for (int k = 0; k < c; ++k) {
-              uint32_t q[8];
-              tmem_ld8(t_lane + k * 8, q);
-              tmem_ld_wait8(q);
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[c & 1][i]));
+          } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) q[i] = pack_bf16(bf16_lo(q[i]) * f, bf16_hi(q[i]) * f);
-              tmem_st8(t_lane + k * 8, q);
+            for (int i = 0; i < 16; ++i) {
+              const int col = c * 16 + i;
+              const bool dead = col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk);
+              mx = fmaxf(mx, dead ? -INFINITY : __uint_as_float(r[c & 1][i]));
             }
           }
-          if (move) {
-            mx = cm;
-            mb = mx * TC_LOG2E;
-          }
+        }
+      }
+      const float mb = mx * TC_LOG2E;
+      // ---- pass 2: P = exp(S - max), row sum; packed bf16 P overwrites S columns already consumed
+      float sum = 0.f;
+      if (warp_active) {
+        tmem_ld16(t_lane, r[0]);
+#pragma unroll
+        for (int c = 0; c < (TC_FK + TC_GK) / 16; ++c) {
+          tmem_ld_wait16(r[c & 1]);
+          if (c + 1 < (TC_FK + TC_GK) / 16) tmem_ld16(t_lane + (c + 1) * 16, r[(c + 1) & 1]);
           uint32_t pk[8];
           float pv[16];
+          if (c * 16 + 16 <= d.L) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = c * 16 + i;
-            const bool dead = !all_live && (col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk));
-            pv[i] = dead ? 0.f : tc_exp2(fmaf(__uint_as_float(r[c & 1][i]), TC_LOG2E, -mb));
-            sum += pv[i];
+            for (int i = 0; i < 16; ++i) {
+              pv[i] = tc_exp2(fmaf(__uint_as_float(r[c & 1][i]), TC_LOG2E, -mb));
+              sum += pv[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c * 16 + i;
+              const bool dead = col < TC_FK ? (col >= d.L) : ((col - TC_FK) >= d.M || mask_gk);
+              pv[i] = dead ? 0.f : tc_exp2(fmaf(__uint_as_float(r[c & 1][i]), TC_LOG2E, -mb));
+              sum += pv[i];
+            }
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
