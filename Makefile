@@ -13,7 +13,7 @@ LIB       := $(LIBDIR)/libxpretrain_b200.so
 
 all: $(LIB)
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/xpretrain_b200.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.inc) $(wildcard $(CSRC)/*.h) include/xpretrain_b200.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 	@grep -E "error|warning|spill" $(OBJDIR)/$*.ptxas.log | grep -v "0 bytes spill" | head -20 || true

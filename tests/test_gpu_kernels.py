@@ -52,7 +52,7 @@ def test_gemm_forward_epilogues(dev, M, N, K):
     assert rel(outf, x.float() @ w.float().t()) < 1e-5
 
 
-@pytest.mark.parametrize("rows,N,K", [(256, 128, 64), (2356 * 2, 768, 3072), (4712, 2304, 768), (64, 512, 768)])
+@pytest.mark.parametrize("rows,N,K", [(256, 128, 64), (2356 * 2, 768, 3072), (4712, 2304, 768), (64, 512, 768), (1000, 320, 776)])
 def test_gemm_dgrad_wgrad(dev, rows, N, K):
     """dx = dy W (MN-major B) with the dQuickGELU epilogue; dW += dy^T x (MN-major A and B, split-K atomics)."""
     from xpretrain_b200 import _lib, ops

@@ -2,6 +2,7 @@
 dgrad(fc2) + dQuickGELU, dgrad(fc1), wgrad(fc1).  CUDA events, L2 flushed between iterations.  XP_GEMM_DEBUG=1 turns the
 epilogue stores off (profiling: how much of a launch is the store traffic)."""
 import json
+import os
 import sys
 
 import torch
@@ -49,7 +50,10 @@ cases = {
     "wgrad fc1 (split-K, fp32 atomics)": (lambda: ops.linear_wgrad(f1, x, dw1), 2.0 * M * I * C),
 }
 out = {}
+only = [t for t in os.environ.get("XP_GEMM_CASES", "").split(",") if t]
 for name, (fn, fl) in cases.items():
+    if only and not any(t in name for t in only):
+        continue
     ms = timeit(fn)
     out[name] = {"ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}
 print(json.dumps(out))

@@ -35,7 +35,8 @@ struct GemmDev {
   float alpha, col_scale;
   int wide;                 // C / aux / residual rows are 32-byte aligned (ld % 16 == 0)
   uint32_t mn_lbo, mn_sbo;  // MN-major descriptor strides (bytes): 64-element atom stride, 8-k-row group stride
-  int dbg;                  // profiling only (XP_GEMM_DEBUG): bit 0 = the epilogue computes but does not store
+  int dbg;                  // profiling only (XP_GEMM_DEBUG): 1 no stores at all, 2 no wait for the staging boxes (racy), 4 stage but
+                            // do not issue the TMA stores, 8 activation = identity, 16 no epilogue input loads, 32 no aux store
   int tma_c, tma_aux;       // pair kernel: C / the aux output leave through shared-memory staging + TMA stores
 };
 
@@ -259,7 +260,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const CUtensorMap& tmX = tmA;
       const int m_tile0 = 0;
       uint32_t st_pairs = 0;
-      (void)stg; (void)tmC; (void)tmX; (void)m_tile0; (void)st_pairs;
+      constexpr bool xin_tma = false, xin_live = false;  // TMA-loaded epilogue input: 2-CTA dGELU kernels only
+      uint64_t* const xbar = nullptr;
+      uint32_t xph = 0;
+      const int num_clusters = 0;
+      auto xin_issue = [](int, int) {};
+      (void)stg; (void)tmC; (void)tmX; (void)m_tile0; (void)st_pairs; (void)xbar; (void)xph; (void)num_clusters; (void)xin_issue;
 #include "gemm_epilogue.inc"
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -489,7 +495,8 @@ extern "C" int xp_gemm(const XpGemm* g, void* stream_v) {
     if (make_tmap_bf16_2d(&t_tmC, g->c, g->N, g->M, g->ldc, 64, 32)) return -1;
     dev.tma_c = 1;
     static const bool tma_aux_off = getenv("XP_GEMM_NO_TMA_AUX") != nullptr;
-    if (g->aux && (g->act == XP_ACT_QUICK_GELU || g->act == XP_ACT_GELU_ERF) && !tma_aux_off) {
+    // aux by TMA: stored by the GELU epilogues, loaded (next tile's boxes, ahead of time) by the dGELU epilogues
+    if (g->aux && g->act != XP_ACT_NONE && splits == 1 && !tma_aux_off) {
       if (make_tmap_bf16_2d(&t_tmX, g->aux, g->N, g->M, g->ld_aux, 64, 32)) return -1;
       dev.tma_aux = 1;
     }
