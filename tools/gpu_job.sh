@@ -1,6 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "gemm" > $O/r02s_t_gemm.log 2>&1; echo "gemm tests rc=$? $(tail -1 $O/r02s_t_gemm.log)"
-timeout 120 python tools/gemm_bench.py > $O/r02s_gemm.log 2>&1
-echo "rc=$? $(tail -1 $O/r02s_gemm.log)"
+run() { name=$1; shift; timeout "$TMO" "$@" > $O/$name.log 2>&1; echo "$name rc=$?"; tail -2 $O/$name.log | cut -c1-600; }
+TMO=900 run r02v_t_all python -m pytest tests -m gpu -q
+TMO=300 run r02v_smoke python -c "import __graft_entry__ as g; g.smoke()"
+TMO=900 run r02v_bench python bench.py --steps 8 --warmup 3
+TMO=600 run r02v_launches ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/r02_launches_step_v2.csv python bench.py --steps 1 --warmup 1

@@ -260,6 +260,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const CUtensorMap& tmX = tmA;
       const int m_tile0 = 0;
       uint32_t st_pairs = 0;
+      constexpr bool kBiasDirect = false;
+      const float* const bias_t = nullptr;
+      (void)bias_t;
       constexpr bool xin_tma = false, xin_live = false;  // TMA-loaded epilogue input: 2-CTA dGELU kernels only
       uint64_t* const xbar = nullptr;
       uint32_t xph = 0;
