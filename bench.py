@@ -396,7 +396,7 @@ def cpu_step_fn(batch):
         out = O.clip_vip_forward(sd, video, ids, mask, cfg)
         loss = O.nce_learnable_temp_loss(out["vis_features"], out["text_features"], sd["logit_scale"])
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return fn
 
 
