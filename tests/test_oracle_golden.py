@@ -264,3 +264,40 @@ def test_swin3d_flop_and_parameter_model_matches_baseline_md():
     assert sum(v.numel() for v in SO.init_state_dict(cfg).values() if v.is_floating_point()) == 89_229_448
     assert abs(SO.flops_per_sample(cfg, 32, 224, 224, include_dead_local_proj=True) / 1e9 - 327.14) < 0.01
     assert abs(SO.flops_per_sample(cfg, 32, 192, 320, include_dead_local_proj=True) / 1e9 - 313.63) < 0.01
+
+
+@pytest.mark.timeout(900)
+def test_full_depth_t12_golden_with_whole_gradient_tensors(golden_dir):
+    """The BENCH model (12 + 12 layers, T = 12, ragged text) with the full gradient tensors the GPU parity test is calibrated
+    on (tests/golden/make_golden.py full12, made from the real reference modules): the oracle replays features, loss, the twelve
+    whole weight-gradient tensors (stored as fp16 after max-normalisation: 2^-11 per element) and every bias / LayerNorm
+    gradient vector in fp32 on the CPU."""
+    gold = torch.load(os.path.join(golden_dir, "full12_b4_t12_ragged.pt"), weights_only=False)
+    meta = gold["meta"]
+    cfg = O.ClipVipCfg()
+    sd = O.init_state_dict(cfg, seed=meta["weight_seed"])
+    video, ids, mask = O.synthetic_batch(meta["B"], meta["T"], meta["Lt"], cfg, seed=meta["data_seed"], ragged_text=True)
+    assert torch.equal(ids, gold["input_ids"]) and torch.equal(mask, gold["attention_mask"])
+    assert abs(float(video.double().sum()) - gold["video_checksum"]) < 1e-6
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    out = O.clip_vip_forward(sd, video, ids, mask, cfg)
+    assert _rel(out["vis_features"].detach(), gold["vis_features"]) < 2e-5
+    assert _rel(out["text_features"].detach(), gold["text_features"]) < 2e-5
+    loss = O.nce_learnable_temp_loss(out["vis_features"], out["text_features"], sd["logit_scale"])
+    assert abs(float(loss.detach()) - float(gold["loss"])) < 2e-5 * abs(float(gold["loss"]))
+    loss.backward()
+    assert len(gold["grad_full"]) >= 12
+    for k, ent in gold["grad_full"].items():
+        want = ent["data"].float() * ent["scale"]
+        if k.endswith("[rows]"):
+            got = sd[k[:-6]].grad[ent["rows"]]
+        elif "[:" in k:
+            name, n = k[:k.index("[:")], int(k[k.index("[:") + 2:-1])
+            got = sd[name].grad[:n]
+        else:
+            got = sd[k].grad
+        assert _rel(got, want) < 1e-3, (k, _rel(got, want))       # fp16 storage of the golden: ~3e-4
+    ref_norm = gold["grad_norms"]["logit_scale"]
+    for k, g in gold["grad_vectors"].items():
+        if float(g.norm()) > 1e-3 * ref_norm:
+            assert _rel(sd[k].grad, g) < 1e-3, (k, _rel(sd[k].grad, g))
